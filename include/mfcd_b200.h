@@ -1,0 +1,235 @@
+/*
+ * mfcd_b200.h -- C ABI of the B200-native (sm_100a) hot path for
+ * MayeulCassier/Matrix-Factorization-With-Comparison-Data.
+ *
+ * The reference is pure Python and has no FFI of its own:
+ * its boundary is the function surface of `structure.py` / `generation_data.py`.
+ * The repo-root modules of the same names keep those signatures and call the
+ * entry points below through ctypes (matrix-factorization-with-comparison-data_b200/_lib.py).
+ * Each entry point names the reference lines (relative to /root/reference) whose
+ * per-call ATen / Python work it replaces.
+ *
+ * Conventions
+ *   - plain `extern "C"`, raw DEVICE pointers + sizes, no torch types;
+ *   - every buffer is owned and allocated by the caller; nothing is retained
+ *     after the call returns (work is enqueued on `stream`, a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream);
+ *   - return 0 on success, MFCD_ERR_* (<0) for bad arguments, a positive
+ *     cudaError_t otherwise; `mfcd_last_error()` gives a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns an error.
+ */
+#ifndef MFCD_B200_H
+#define MFCD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFCD_ABI_VERSION 1
+
+#define MFCD_OK 0
+#define MFCD_ERR_ARG (-1)
+#define MFCD_ERR_WORKSPACE (-2)
+#define MFCD_ERR_UNSUPPORTED (-3)
+
+/* One labelled comparison: user u prefers item i over item j with label z
+ * (hard 0/1 or a soft label in [0,1]).  16 bytes, moved with one 128-bit load.
+ * Replaces the python tuples of BTLPreferenceDataset.data (structure.py:507-519)
+ * and the int64/int64/int64/float64 batches default_collate builds from them. */
+typedef struct mfcd_triplet {
+  int32_t u, i, j;
+  float z;
+} mfcd_triplet;
+
+/* Ground-truth matrix X as the kernels see it: either a dense row-major fp32
+ * matrix (X != NULL, leading dimension ldx) or a low-rank product
+ * X[u][i] = scale * <A[u,:], B[i,:]> (X == NULL; A is n x dx, B is m x dx). */
+typedef struct mfcd_xview {
+  const float* X;
+  int64_t ldx;
+  const float* A;
+  const float* B;
+  int32_t dx;
+  float scale;
+} mfcd_xview;
+
+/* ---- library / device info ------------------------------------------------ */
+int mfcd_abi_version(void);
+const char* mfcd_last_error(void);
+int mfcd_device_sm_count(int* out);
+
+/* ---- data staging ---------------------------------------------------------- */
+/* int64 u,i,j + float64 z columns (what the reference's DataLoader yields,
+ * structure.py:846) -> 16-byte records. */
+int mfcd_pack_triplets(const int64_t* u, const int64_t* i, const int64_t* j, const double* z,
+                       int64_t N, mfcd_triplet* out, void* stream);
+int mfcd_unpack_triplets(const mfcd_triplet* rec, int64_t N, int64_t* u, int64_t* i, int64_t* j,
+                         double* z, void* stream);
+/* out[k] = rec[perm[k]] for k in [0,N): materialise one epoch's shuffled order
+ * (replaces RandomSampler + default_collate, structure.py:738, :845). */
+int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N, mfcd_triplet* out,
+                         void* stream);
+
+/* ---- K1: fused forward + BCE + backward, atomic scatter --------------------
+ * Replaces structure.py:848-850 (model forward :787-795, F.binary_cross_entropy,
+ * loss.backward()) for the batch rec[perm[start..start+B)] (perm may be NULL =
+ * identity).  U is n x d, V is m x d, row-major fp32.  Adds the batch's dense
+ * gradients into gU / gV with red.global.add (they must hold zeros, or the sum
+ * being accumulated) and adds  sum_b BCE_b * inv_batch  to *loss.
+ * inv_batch = 1 / (global batch size): 1/B on one GPU, 1/(B*world) under
+ * data-parallel training. */
+int mfcd_triplet_fwd_bwd(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                         int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
+                         float* loss, void* stream);
+
+/* ---- K1+K2: deterministic variant ------------------------------------------
+ * Same contract, but run-to-run bit-reproducible: per-row gradient sums are
+ * formed by sorting the batch by destination row (stable, so batch order is
+ * kept inside a row, the order the reference's CPU index_put_ uses) and a
+ * segmented reduction; the loss is reduced in a fixed order. */
+int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes);
+int mfcd_triplet_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                             int64_t start, int64_t B, int32_t d, float inv_batch, int64_t n_users,
+                             int64_t n_items, float* gU, float* gV, float* loss, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ---- K3: fused dense optimiser update --------------------------------------
+ * torch.optim.Adam single-tensor semantics with coupled L2 (structure.py:364,
+ * :851): g += wd*p; m += (g-m)(1-b1); v = b2*v + (1-b2)g*g;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), t = step (1-based).
+ * With zero_grad != 0 the gradient buffer is cleared in the same pass
+ * (optimizer.zero_grad(), structure.py:847). */
+int mfcd_adam_update(float* p, float* g, float* m, float* v, int64_t numel, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, int32_t zero_grad,
+                     void* stream);
+/* torch.optim.SGD (dampening 0, no nesterov); buf may be NULL when momentum == 0. */
+int mfcd_sgd_update(float* p, float* g, float* buf, int64_t numel, float lr, float momentum,
+                    float weight_decay, int64_t step, int32_t zero_grad, void* stream);
+
+/* ---- one training epoch, launched from C ------------------------------------
+ * The inner loop of train_model (structure.py:845-852) for one epoch on one GPU:
+ * for each batch k: K1 (atomic or deterministic) then K3, with the batch-mean
+ * loss written to step_losses[k] (device, n_steps floats, pre-zeroed by the
+ * call).  Tables, gradients and optimiser state are one flat buffer each,
+ * U first then V: params[0 .. n_users*d) is U, the rest is V. */
+#define MFCD_OPT_ADAM 0
+#define MFCD_OPT_SGD 1
+#define MFCD_MODE_ATOMIC 0
+#define MFCD_MODE_DETERMINISTIC 1
+typedef struct mfcd_epoch_args {
+  float* params;
+  float* grads;
+  float* state1; /* Adam exp_avg / SGD momentum buffer */
+  float* state2; /* Adam exp_avg_sq / unused */
+  int64_t n_users, n_items;
+  int32_t d;
+  int32_t optimizer;
+  int32_t mode;
+  int32_t reserved;
+  const mfcd_triplet* rec;
+  const int32_t* perm; /* epoch order, length n_samples, or NULL */
+  int64_t n_samples;
+  int64_t batch_size;
+  float lr, beta1, beta2, eps, weight_decay, momentum;
+  int64_t step0; /* optimiser steps already taken before this epoch */
+  float* step_losses;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} mfcd_epoch_args;
+int mfcd_train_epoch(const mfcd_epoch_args* args);
+
+/* ---- K4: evaluation ----------------------------------------------------------
+ * evaluate_model (structure.py:896-921) and the validation pass of train_model
+ * (:858-868): batch_loss[b] = mean BCE of batch b (batches of batch_size in
+ * record order, last one ragged), *correct += #{(p > 0.5) == z}. */
+int mfcd_triplet_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int32_t d,
+                      int64_t batch_size, float* batch_loss, unsigned long long* correct, void* stream);
+/* compute_ground_truth_metrics (structure.py:1100-1127): per-batch mean of
+ * (sigmoid(X[u,i]-X[u,j]) - z)^2 (no scale s) and #{(diff > 0) == z}. */
+int mfcd_ground_truth_eval(const mfcd_xview* X, const mfcd_triplet* rec, int64_t N, int64_t batch_size,
+                           float* batch_mse, unsigned long long* correct, void* stream);
+/* MatrixFactorization.forward (structure.py:773-795): p[k] = sigmoid(<U_u, V_i - V_j>). */
+int mfcd_triplet_scores(const float* U, const float* V, const int64_t* u, const int64_t* i,
+                        const int64_t* j, int64_t N, int32_t d, float* p, void* stream);
+
+/* ---- K7: triplet candidate samplers ------------------------------------------
+ * Candidate c of a round uses Philox4x32-10 at (seed, counter0 + c): it is a
+ * pure function of (seed, counter), so rounds and ranks draw disjoint streams.
+ * Each writes keys[c] = (u*m + i)*m + j, or MFCD_KEY_NONE when the candidate
+ * fails the strategy's own test (i == j, margin, ...).
+ *   random     : generation_data.py:16-26   u ~ U[0,n), i,j ~ U[0,m)
+ *   margin     : generation_data.py:46-84   + |X[u,i]-X[u,j]| <= margin
+ *   popularity : generation_data.py:103-128 i ~ probs, j ~ probs without i (cdf = inclusive fp64 prefix sums, cdf[m-1] = total)
+ *   svd block  : generation_data.py:164-174 u ~ U(top_users), i != j ~ U(top_items)
+ */
+#define MFCD_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+int mfcd_sample_random(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                       uint64_t* keys, void* stream);
+int mfcd_sample_margin(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                       const mfcd_xview* X, float margin, uint64_t* keys, void* stream);
+int mfcd_sample_popularity(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                           const double* cdf, uint64_t* keys, void* stream);
+int mfcd_sample_block(int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                      const int32_t* top_users, int64_t n_top_users, const int32_t* top_items,
+                      int64_t n_top_items, uint64_t* keys, void* stream);
+
+/* Sequential "accept if new" over a candidate stream, done with a stable sort:
+ * candidate c is accepted iff keys[c] != NONE, it equals no seen[] key and no
+ * earlier candidate; the first `want` accepted keys are written, in stream
+ * order, to out[0..*n_out).  Same result as the reference's python set loop
+ * run over the same candidates (generation_data.py:24-25). */
+int mfcd_unique_workspace_bytes(int64_t n_seen, int64_t count, size_t* bytes);
+int mfcd_unique_accept(const uint64_t* seen, int64_t n_seen, const uint64_t* keys, int64_t count,
+                       int64_t want, uint64_t* out, int64_t* n_out /* device */, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- K8: BTL label sampler ------------------------------------------------------
+ * BTLPreferenceDataset._generate_labels (structure.py:507-519).  For triplet t
+ * (key[t], decoded with m): q = sigmoid(scale*(X[u,i]-X[u,j])); draw k is
+ * `uniform(t,k) < q` with uniform(t,k) the 24-bit uniform of Philox word
+ * (t*K+k) (word w = component w%4 of Philox(seed, w/4)).
+ * soft == 0: writes N*K records, the K copies of a triplet consecutive;
+ * soft != 0: writes N records with z = mean of the K draws.
+ * If `uniforms` is non-NULL (N*K floats) they are used instead of Philox:
+ * replaying host uniforms gives the host's labels bit for bit. */
+int mfcd_btl_labels(const mfcd_xview* X, const uint64_t* keys, int64_t N, int64_t m, int32_t K,
+                    float scale, int32_t soft, uint64_t seed, const float* uniforms, mfcd_triplet* out,
+                    void* stream);
+/* word-exact view of the generator above, for tests: out[w] = 24-bit uniform of word w0+w */
+int mfcd_philox_uniforms(uint64_t seed, uint64_t w0, int64_t count, float* out, void* stream);
+
+/* ---- K5: reconstruction statistics ------------------------------------------------
+ * One pass over W = U V^T (never materialised) and X for compute_reconstruction_error
+ * (structure.py:939-955) and compute_alpha_and_norm_ratios (:980-1064).
+ * row_stats[r*8 + k], fp64, for row r with x = X[r,:], w = W[r,:], a = <U_r, vbar>
+ * (row mean of W), b_c = <ubar, V_c> (column mean of W):
+ *   0: sum x   1: sum x^2   2: sum (w-a)   3: sum (w-a)^2   4: sum x (w-a)
+ *   5: sum (w - b_c - s x)^2   6: a   7: unused
+ * ubar[d] / vbar[d] are the column means of U and V (fp32, device). */
+int mfcd_table_col_means(const float* T, int64_t rows, int32_t d, float* mean, void* stream);
+int mfcd_recon_stats(const float* U, const float* V, int64_t n, int64_t m, int32_t d, const mfcd_xview* X,
+                     float s, const float* ubar, const float* vbar, double* row_stats, void* stream);
+/* rows [r0, r0+nr) of W = U V^T into out (nr x m, row-major): structure.py:389-392
+ * sampled rows, and the row blocks the Spearman pass ranks. */
+int mfcd_reconstruct_rows(const float* U, const float* V, int64_t r0, int64_t nr, int64_t m, int32_t d,
+                          float* out, void* stream);
+int mfcd_xview_rows(const mfcd_xview* X, int64_t r0, int64_t nr, int64_t m, float* out, void* stream);
+
+/* ---- K6: row ranks for Spearman -----------------------------------------------------
+ * scipy.stats.spearmanr semantics (structure.py:1024-1031): ranks[r][c] = 1-based
+ * rank of vals[r][c] within its row, ties sharing their average rank.
+ * Then rho[r] = Pearson(rank_a[r,:], rank_b[r,:]) in fp64. */
+int mfcd_rank_workspace_bytes(int64_t rows, int64_t m, size_t* bytes);
+int mfcd_row_ranks(const float* vals, int64_t rows, int64_t m, float* ranks, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int mfcd_row_pearson(const float* a, const float* b, int64_t rows, int64_t m, double* rho, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFCD_B200_H */

@@ -1,0 +1,103 @@
+// Library plumbing: error strings, device info, record packing / gathering.
+#include "common.cuh"
+
+namespace mfcd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return (int)e;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached = v;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+__global__ void k_pack(const int64_t* __restrict__ u, const int64_t* __restrict__ i,
+                       const int64_t* __restrict__ j, const double* __restrict__ z, int64_t N,
+                       mfcd_triplet* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    int4 r;
+    r.x = (int)u[k]; r.y = (int)i[k]; r.z = (int)j[k];
+    r.w = __float_as_int((float)z[k]);          // z.float(), structure.py:849
+    reinterpret_cast<int4*>(out)[k] = r;
+  }
+}
+
+__global__ void k_unpack(const mfcd_triplet* __restrict__ rec, int64_t N, int64_t* u, int64_t* i, int64_t* j,
+                         double* z) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    int4 r = __ldg(reinterpret_cast<const int4*>(rec) + k);
+    u[k] = r.x; i[k] = r.y; j[k] = r.z; z[k] = (double)__int_as_float(r.w);
+  }
+}
+
+__global__ void k_gather(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict__ perm, int64_t N,
+                         mfcd_triplet* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    reinterpret_cast<int4*>(out)[k] = __ldg(reinterpret_cast<const int4*>(rec) + perm[k]);
+  }
+}
+
+}  // namespace mfcd
+
+using namespace mfcd;
+
+extern "C" int mfcd_abi_version(void) { return MFCD_ABI_VERSION; }
+extern "C" const char* mfcd_last_error(void) { return g_err; }
+
+extern "C" int mfcd_device_sm_count(int* out) {
+  MFCD_REQUIRE(out != nullptr, "mfcd_device_sm_count: out is NULL");
+  int dev = 0;
+  MFCD_CUDA(cudaGetDevice(&dev));
+  MFCD_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_pack_triplets(const int64_t* u, const int64_t* i, const int64_t* j, const double* z,
+                                  int64_t N, mfcd_triplet* out, void* stream) {
+  MFCD_REQUIRE(N >= 0, "mfcd_pack_triplets: N < 0");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(u && i && j && z && out, "mfcd_pack_triplets: NULL pointer");
+  k_pack<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(u, i, j, z, N, out);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_unpack_triplets(const mfcd_triplet* rec, int64_t N, int64_t* u, int64_t* i, int64_t* j,
+                                    double* z, void* stream) {
+  MFCD_REQUIRE(N >= 0, "mfcd_unpack_triplets: N < 0");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(rec && u && i && j && z, "mfcd_unpack_triplets: NULL pointer");
+  k_unpack<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(rec, N, u, i, j, z);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N, mfcd_triplet* out,
+                                    void* stream) {
+  MFCD_REQUIRE(N >= 0, "mfcd_gather_triplets: N < 0");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(rec && perm && out, "mfcd_gather_triplets: NULL pointer");
+  k_gather<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(rec, perm, N, out);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}

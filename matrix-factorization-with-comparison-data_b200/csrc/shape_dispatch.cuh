@@ -1,0 +1,108 @@
+// Row-shape dispatch shared by every kernel that walks embedding rows.
+//
+// A row of d floats is covered by LPT lanes (a lane-aligned sub-warp group,
+// LPT a power of two), each lane moving VEC floats per access (VEC = 4, 2 or 1
+// depending on the alignment d allows), NITER accesses per lane:
+//     d = 64  -> VEC 4, LPT 16, NITER 1   (two triplets per warp side by side)
+//     d = 10  -> VEC 2, LPT 8 (5 active), NITER 1
+//     d = 2   -> VEC 2, LPT 1
+//     d = 128 -> VEC 4, LPT 32, NITER 1 ;  d = 256 -> NITER 2
+#pragma once
+#include "common.cuh"
+
+namespace mfcd {
+
+struct RowShape {
+  int vec, lpt, niter;
+};
+
+static inline bool row_shape_for(int d, RowShape* s) {
+  if (d <= 0) return false;
+  int vec = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;
+  int chunks = d / vec;
+  int lpt = 1;
+  while (lpt < chunks && lpt < 32) lpt <<= 1;
+  int niter = (chunks + lpt - 1) / lpt;
+  if (niter > 4) return false;
+  s->vec = vec; s->lpt = lpt; s->niter = niter;
+  return true;
+}
+
+// L is a class template L<VEC, LPT, NITER> with a static `int run(Args...)`.
+#define MFCD_DISPATCH_LPT(L, VEC, ...)                                      \
+  switch (shape.lpt) {                                                      \
+    case 1:  return L<VEC, 1, 1>::run(__VA_ARGS__);                         \
+    case 2:  return L<VEC, 2, 1>::run(__VA_ARGS__);                         \
+    case 4:  return L<VEC, 4, 1>::run(__VA_ARGS__);                         \
+    case 8:  return L<VEC, 8, 1>::run(__VA_ARGS__);                         \
+    case 16: return L<VEC, 16, 1>::run(__VA_ARGS__);                        \
+    default:                                                                \
+      switch (shape.niter) {                                                \
+        case 1:  return L<VEC, 32, 1>::run(__VA_ARGS__);                    \
+        case 2:  return L<VEC, 32, 2>::run(__VA_ARGS__);                    \
+        case 3:  return L<VEC, 32, 3>::run(__VA_ARGS__);                    \
+        default: return L<VEC, 32, 4>::run(__VA_ARGS__);                    \
+      }                                                                     \
+  }
+
+#define MFCD_DISPATCH_ROW_SHAPE(L, d, ...)                                  \
+  do {                                                                      \
+    ::mfcd::RowShape shape;                                                 \
+    if (!::mfcd::row_shape_for((d), &shape)) {                              \
+      ::mfcd::set_error("unsupported embedding width d=%d (need d <= 512 for d%%4==0, <= 256 for even d, <= 128 otherwise)", (int)(d)); \
+      return MFCD_ERR_UNSUPPORTED;                                          \
+    }                                                                       \
+    if (shape.vec == 4) { MFCD_DISPATCH_LPT(L, 4, __VA_ARGS__) }            \
+    else if (shape.vec == 2) { MFCD_DISPATCH_LPT(L, 2, __VA_ARGS__) }       \
+    else { MFCD_DISPATCH_LPT(L, 1, __VA_ARGS__) }                           \
+  } while (0)
+
+// Per-lane register image of one triplet's rows: u-row fragment(s) and the
+// fragment(s) of V[i]-V[j].
+template <int VEC, int LPT, int NITER>
+struct TripletRows {
+  Frag<VEC> uu[NITER];
+  Frag<VEC> dv[NITER];
+};
+
+template <int VEC, int LPT, int NITER>
+__device__ __forceinline__ void load_rows(TripletRows<VEC, LPT, NITER>& t, const float* __restrict__ U,
+                                          const float* __restrict__ V, int tu, int ti, int tj, int d,
+                                          int sub, bool ok) {
+  const float* pu = U + static_cast<int64_t>(tu) * d;
+  const float* pi = V + static_cast<int64_t>(ti) * d;
+  const float* pj = V + static_cast<int64_t>(tj) * d;
+#pragma unroll
+  for (int it = 0; it < NITER; ++it) {
+    const int c = (it * LPT + sub) * VEC;
+    if (ok && c < d) {
+      t.uu[it] = ldg_frag<VEC>(pu + c);
+      Frag<VEC> a = ldg_frag<VEC>(pi + c);
+      Frag<VEC> b = ldg_frag<VEC>(pj + c);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) t.dv[it].v[k] = a.v[k] - b.v[k];
+    } else {
+      t.uu[it] = frag_zero<VEC>();
+      t.dv[it] = frag_zero<VEC>();
+    }
+  }
+}
+
+// lane-partial of <U_u, V_i - V_j>
+template <int VEC, int LPT, int NITER>
+__device__ __forceinline__ float partial_dot(const TripletRows<VEC, LPT, NITER>& t) {
+  float acc = 0.f;
+#pragma unroll
+  for (int it = 0; it < NITER; ++it)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc = fmaf(t.uu[it].v[k], t.dv[it].v[k], acc);
+  return acc;
+}
+
+template <int LPT>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+  if constexpr (LPT == 32) return 0xffffffffu;
+  else return ((1u << LPT) - 1u) << ((lane / LPT) * LPT);
+}
+
+}  // namespace mfcd

@@ -1,0 +1,180 @@
+// K4: evaluation kernels (no gradients).
+//   mfcd_triplet_eval       evaluate_model (structure.py:896-921) and the validation
+//                           pass of train_model (structure.py:858-868)
+//   mfcd_ground_truth_eval  compute_ground_truth_metrics (structure.py:1100-1127)
+//   mfcd_triplet_scores     MatrixFactorization.forward (structure.py:773-795)
+// The reference reports "mean over batches of the batch-mean loss", so the
+// kernels produce one mean per batch of `batch_size` consecutive records.
+#include "internal.h"
+#include "shape_dispatch.cuh"
+
+namespace mfcd {
+
+constexpr int kEvalBlock = 256;
+
+template <int VEC, int LPT, int NITER>
+__global__ void __launch_bounds__(kEvalBlock)
+k_eval(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec, int64_t N,
+       int d, int64_t batch_size, float* __restrict__ batch_loss, unsigned long long* __restrict__ correct) {
+  constexpr int GPW = 32 / LPT;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+  const unsigned gmask = group_mask<LPT>(lane);
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nb = (N + batch_size - 1) / batch_size;
+  unsigned int hits = 0;
+
+  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+    const int64_t k = base + lane;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (k < N) r = __ldg(reinterpret_cast<const int4*>(rec) + k);
+    const int nvalid = (N - base) < 32 ? (int)(N - base) : 32;
+#pragma unroll 2
+    for (int rr = 0; rr < LPT; ++rr) {
+      const int e = rr * GPW + grp;
+      const int tu = __shfl_sync(0xffffffffu, r.x, e);
+      const int ti = __shfl_sync(0xffffffffu, r.y, e);
+      const int tj = __shfl_sync(0xffffffffu, r.z, e);
+      const float z = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+      const bool ok = e < nvalid;
+      TripletRows<VEC, LPT, NITER> rows;
+      load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
+      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
+      if (ok && sub == 0) {
+        const float p = sigmoidf_ref(x);
+        const int64_t pos = base + e;
+        const int64_t b = pos / batch_size;
+        const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
+        atomicAdd(batch_loss + b, bce_ref(p, z) / (float)cnt);
+        const float hard = (p > 0.5f) ? 1.f : 0.f;           // (pred > 0.5).float() == z
+        hits += (hard == z) ? 1u : 0u;
+      }
+    }
+  }
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  if (lane == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
+}
+
+template <int VEC, int LPT, int NITER>
+struct EvalLauncher {
+  static int run(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int d, int64_t batch_size,
+                 float* batch_loss, unsigned long long* correct, cudaStream_t st) {
+    const int grid = grid_for(N, kEvalBlock, 4);
+    k_eval<VEC, LPT, NITER><<<grid, kEvalBlock, 0, st>>>(U, V, rec, N, d, batch_size, batch_loss, correct);
+    MFCD_CHECK_LAUNCH();
+    return MFCD_OK;
+  }
+};
+
+static int launch_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int d,
+                       int64_t batch_size, float* batch_loss, unsigned long long* correct, cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(EvalLauncher, d, U, V, rec, N, d, batch_size, batch_loss, correct, st);
+}
+
+__global__ void __launch_bounds__(256)
+k_gt_eval(mfcd_xview X, const mfcd_triplet* __restrict__ rec, int64_t N, int64_t batch_size,
+          float* __restrict__ batch_mse, unsigned long long* __restrict__ correct) {
+  const int64_t nb = (N + batch_size - 1) / batch_size;
+  unsigned int hits = 0;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + k);
+    const float z = __int_as_float(r.w);
+    const float diff = xview_at(X, r.x, r.y) - xview_at(X, r.x, r.z);   // no scale s (structure.py:1108)
+    const float e = sigmoidf_ref(diff) - z;
+    const int64_t b = k / batch_size;
+    const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
+    atomicAdd(batch_mse + b, e * e / (float)cnt);
+    const float hard = (diff > 0.f) ? 1.f : 0.f;
+    hits += (hard == z) ? 1u : 0u;
+  }
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
+}
+
+template <int VEC, int LPT, int NITER>
+__global__ void __launch_bounds__(kEvalBlock)
+k_scores(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
+         const int64_t* __restrict__ i, const int64_t* __restrict__ j, int64_t N, int d, float* __restrict__ p) {
+  constexpr int GPW = 32 / LPT;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+  const unsigned gmask = group_mask<LPT>(lane);
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+    const int64_t k = base + lane;
+    int ru = 0, ri = 0, rj = 0;
+    if (k < N) { ru = (int)u[k]; ri = (int)i[k]; rj = (int)j[k]; }
+    const int nvalid = (N - base) < 32 ? (int)(N - base) : 32;
+    for (int rr = 0; rr < LPT; ++rr) {
+      const int e = rr * GPW + grp;
+      const int tu = __shfl_sync(0xffffffffu, ru, e);
+      const int ti = __shfl_sync(0xffffffffu, ri, e);
+      const int tj = __shfl_sync(0xffffffffu, rj, e);
+      const bool ok = e < nvalid;
+      TripletRows<VEC, LPT, NITER> rows;
+      load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
+      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
+      if (ok && sub == 0) p[base + e] = sigmoidf_ref(x);
+    }
+  }
+}
+
+template <int VEC, int LPT, int NITER>
+struct ScoresLauncher {
+  static int run(const float* U, const float* V, const int64_t* u, const int64_t* i, const int64_t* j, int64_t N,
+                 int d, float* p, cudaStream_t st) {
+    const int grid = grid_for(N, kEvalBlock, 4);
+    k_scores<VEC, LPT, NITER><<<grid, kEvalBlock, 0, st>>>(U, V, u, i, j, N, d, p);
+    MFCD_CHECK_LAUNCH();
+    return MFCD_OK;
+  }
+};
+
+static int launch_scores(const float* U, const float* V, const int64_t* u, const int64_t* i, const int64_t* j,
+                         int64_t N, int d, float* p, cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(ScoresLauncher, d, U, V, u, i, j, N, d, p, st);
+}
+
+}  // namespace mfcd
+
+using namespace mfcd;
+
+static int check_xview(const char* fn, const mfcd_xview* X) {
+  MFCD_REQUIRE(X != nullptr, "%s: xview is NULL", fn);
+  MFCD_REQUIRE(X->X != nullptr || (X->A != nullptr && X->B != nullptr && X->dx >= 1),
+               "%s: xview has neither a dense matrix nor factors", fn);
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int32_t d,
+                                 int64_t batch_size, float* batch_loss, unsigned long long* correct,
+                                 void* stream) {
+  MFCD_REQUIRE(N >= 0 && d >= 1 && batch_size >= 1, "mfcd_triplet_eval: bad sizes");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(U && V && rec && batch_loss && correct, "mfcd_triplet_eval: NULL pointer");
+  return launch_eval(U, V, rec, N, d, batch_size, batch_loss, correct, as_stream(stream));
+}
+
+extern "C" int mfcd_ground_truth_eval(const mfcd_xview* X, const mfcd_triplet* rec, int64_t N, int64_t batch_size,
+                                      float* batch_mse, unsigned long long* correct, void* stream) {
+  int rc = check_xview("mfcd_ground_truth_eval", X);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(N >= 0 && batch_size >= 1, "mfcd_ground_truth_eval: bad sizes");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(rec && batch_mse && correct, "mfcd_ground_truth_eval: NULL pointer");
+  k_gt_eval<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(*X, rec, N, batch_size, batch_mse, correct);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_scores(const float* U, const float* V, const int64_t* u, const int64_t* i,
+                                   const int64_t* j, int64_t N, int32_t d, float* p, void* stream) {
+  MFCD_REQUIRE(N >= 0 && d >= 1, "mfcd_triplet_scores: bad sizes");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(U && V && u && i && j && p, "mfcd_triplet_scores: NULL pointer");
+  return launch_scores(U, V, u, i, j, N, d, p, as_stream(stream));
+}

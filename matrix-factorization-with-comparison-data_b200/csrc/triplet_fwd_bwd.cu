@@ -1,0 +1,403 @@
+// K1: fused forward + BCE + backward for one batch of comparison triplets.
+//
+// Replaces, per optimiser step of the reference (structure.py:848-850):
+//   pred = sigmoid(sum(U[u] * (V[i] - V[j]), dim=1))        structure.py:787-795
+//   loss = F.binary_cross_entropy(pred, z.float())           structure.py:849
+//   loss.backward()   -> dense U.grad / V.grad               structure.py:850
+//
+// Layout: a lane-aligned sub-warp group of LPT lanes owns one triplet; each
+// lane holds VEC consecutive floats of the three rows (128-bit loads when
+// d % 4 == 0).  A warp loads 32 consecutive 16-byte records with one coalesced
+// LDG.128 per lane and broadcasts the indices with shuffles; UNR triplets per
+// group are kept in flight so that 3*UNR row loads overlap.  Gradients leave as
+// REDG.E.ADD.F32x4 (fast mode) -- HBM/L2-bound byte traffic, no tensor cores.
+//
+// Algorithmic bytes per triplet: 16 (record) + 3*4*d (row reads) + 3*4*d
+// (gradient row updates) = 16 + 24 d.
+#include "internal.h"
+#include "shape_dispatch.cuh"
+
+namespace mfcd {
+
+constexpr int kBlock = 256;
+
+// sums a per-thread fp32 value over the block (all threads must call)
+__device__ __forceinline__ float block_sum_256(float x, float* smem8) {
+  x = warp_sum(x);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem8[w] = x;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = (lane < (kBlock / 32)) ? smem8[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+
+// MODE 0: atomic scatter into gU/gV.  MODE 1: write g_b to gbuf (deterministic path).
+template <int VEC, int LPT, int NITER, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
+          const int32_t* __restrict__ perm, int64_t start, int64_t B, int d, float inv_batch,
+          float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ gbuf,
+          float* __restrict__ loss_out /* MODE 0: scalar accumulator; MODE 1: per-block partials */) {
+  constexpr int GPW = 32 / LPT;                                   // triplets side by side in a warp
+  constexpr int UNR = (NITER > 1) ? 2 : (LPT >= 4 ? 4 : LPT);     // triplets in flight per group
+  __shared__ float s_red[kBlock / 32];
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+  const unsigned gmask = group_mask<LPT>(lane);
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  float loss_acc = 0.f;
+  for (int64_t base = warp0 * 32; base < B; base += nwarps * 32) {
+    const int64_t k = base + lane;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (k < B) {
+      const int64_t idx = perm ? (int64_t)__ldg(perm + start + k) : (start + k);
+      r = __ldg(reinterpret_cast<const int4*>(rec) + idx);
+    }
+    const int nvalid = (B - base) < 32 ? (int)(B - base) : 32;
+
+#pragma unroll 1
+    for (int r0 = 0; r0 < LPT; r0 += UNR) {
+      TripletRows<VEC, LPT, NITER> rows[UNR];
+      int tu[UNR], ti[UNR], tj[UNR];
+      float tz[UNR];
+      bool ok[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int e = (r0 + q) * GPW + grp;                      // tile slot this group handles
+        tu[q] = __shfl_sync(0xffffffffu, r.x, e);
+        ti[q] = __shfl_sync(0xffffffffu, r.y, e);
+        tj[q] = __shfl_sync(0xffffffffu, r.z, e);
+        tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+        ok[q] = e < nvalid;
+        load_rows<VEC, LPT, NITER>(rows[q], U, V, tu[q], ti[q], tj[q], d, sub, ok[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows[q]), gmask);
+        const float p = sigmoidf_ref(x);
+        const float g = bce_grad_score_ref(p, tz[q], inv_batch);
+        if (ok[q]) {
+          if (sub == 0) loss_acc += bce_ref(p, tz[q]);
+          if (MODE == 1) {
+            if (sub == 0) gbuf[base + (r0 + q) * GPW + grp] = g;
+          } else if (g != 0.f) {
+            float* du = gU + (int64_t)tu[q] * d;
+            float* di = gV + (int64_t)ti[q] * d;
+            float* dj = gV + (int64_t)tj[q] * d;
+#pragma unroll
+            for (int it = 0; it < NITER; ++it) {
+              const int c = (it * LPT + sub) * VEC;
+              if (c < d) {
+                Frag<VEC> a, b, nb;
+#pragma unroll
+                for (int kk = 0; kk < VEC; ++kk) {
+                  a.v[kk] = g * rows[q].dv[it].v[kk];
+                  b.v[kk] = g * rows[q].uu[it].v[kk];
+                  nb.v[kk] = -b.v[kk];
+                }
+                red_frag<VEC>(du + c, a);
+                red_frag<VEC>(di + c, b);
+                red_frag<VEC>(dj + c, nb);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  const float tot = block_sum_256(loss_acc, s_red);
+  if (threadIdx.x == 0) {
+    if (MODE == 0) atomicAdd(loss_out, tot * inv_batch);
+    else loss_out[blockIdx.x] = tot;
+  }
+}
+
+template <int VEC, int LPT, int NITER>
+struct AtomicLauncher {
+  static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                 int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss, cudaStream_t st) {
+    const int grid = grid_for(B, kBlock, 4);           // a block pass covers 8 warp tiles of 32 triplets
+    k_fwd_bwd<VEC, LPT, NITER, 0><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV,
+                                                            nullptr, loss);
+    MFCD_CHECK_LAUNCH();
+    return MFCD_OK;
+  }
+};
+
+int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                          int64_t start, int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss,
+                          cudaStream_t st) {
+  if (B == 0) return MFCD_OK;
+  MFCD_DISPATCH_ROW_SHAPE(AtomicLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, st);
+}
+
+// ===========================================================================
+// Deterministic mode
+// ===========================================================================
+// (a) B <= kSmallB: ONE CTA does the whole batch.  Indices, g_b and losses sit
+//     in shared memory; the owner of a destination row is the first batch
+//     entry that names it, and it sums that row's contributions in batch order
+//     -- exactly the order of the reference's sequential index_put_.
+// (b) larger B: g_b from the MODE 1 forward, three stable radix sorts of
+//     (row, b) pairs, and a chunked segmented reduction staged through shared
+//     memory with a fix-up pass for rows that straddle chunks.
+constexpr int kSmallB = 256;
+
+template <int VEC, int LPT, int NITER>
+__global__ void __launch_bounds__(kBlock)
+k_det_small(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
+            const int32_t* __restrict__ perm, int64_t start, int B, int d, float inv_batch,
+            float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ loss_out) {
+  __shared__ int su[kSmallB], si[kSmallB], sj[kSmallB];
+  __shared__ float sg[kSmallB], sl[kSmallB];
+  constexpr int NG = kBlock / LPT;            // groups in the CTA
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int gid = threadIdx.x / LPT;
+  const unsigned gmask = group_mask<LPT>(lane);
+
+  for (int b = threadIdx.x; b < B; b += kBlock) {
+    const int64_t idx = perm ? (int64_t)perm[start + b] : (start + b);
+    const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + idx);
+    su[b] = r.x; si[b] = r.y; sj[b] = r.z; sg[b] = __int_as_float(r.w);   // sg holds z until phase 1 ends
+  }
+  __syncthreads();
+
+  // phase 1: forward, g_b, per-sample loss   (uniform trip count per group)
+  const int rounds = (B + NG - 1) / NG;
+  for (int rr = 0; rr < rounds; ++rr) {
+    const int b = rr * NG + gid;
+    const bool ok = b < B;
+    TripletRows<VEC, LPT, NITER> rows;
+    const int tu = ok ? su[b] : 0, ti = ok ? si[b] : 0, tj = ok ? sj[b] : 0;
+    const float z = ok ? sg[b] : 0.f;
+    load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
+    const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
+    const float p = sigmoidf_ref(x);
+    __syncwarp(gmask);
+    if (ok && sub == 0) {
+      sl[b] = bce_ref(p, z);
+      sg[b] = bce_grad_score_ref(p, z, inv_batch);
+    }
+  }
+  __syncthreads();
+
+  // loss: fixed-order reduction by warp 0
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+    for (int b = lane; b < B; b += 32) t += sl[b];
+    t = warp_sum(t);
+    if (lane == 0) *loss_out += t * inv_batch;
+  }
+
+  // phase 2: gU rows.  Entry b owns row su[b] iff no earlier entry names it.
+  for (int b = gid; b < B; b += NG) {
+    const int row = su[b];
+    bool first = true;
+    for (int t = 0; t < b; ++t) first = first && (su[t] != row);
+    if (!first) continue;
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) {
+      const int c = (it * LPT + sub) * VEC;
+      if (c >= d) continue;
+      Frag<VEC> acc = frag_zero<VEC>();
+      for (int t = b; t < B; ++t) {
+        if (su[t] != row) continue;
+        const float g = sg[t];
+        Frag<VEC> a = ldg_frag<VEC>(V + (int64_t)si[t] * d + c);
+        Frag<VEC> bb = ldg_frag<VEC>(V + (int64_t)sj[t] * d + c);
+#pragma unroll
+        for (int kk = 0; kk < VEC; ++kk) acc.v[kk] += g * (a.v[kk] - bb.v[kk]);
+      }
+      float* dst = gU + (int64_t)row * d + c;
+      Frag<VEC> cur = ld_frag<VEC>(dst);
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc.v[kk];
+      st_frag<VEC>(dst, cur);
+    }
+  }
+
+  // phase 3: gV rows.  A row can be named as i or as j; its owner is the first
+  // entry naming it either way.  sum_i and sum_j are formed separately in
+  // batch order and then added (autograd adds the two index_put_ results).
+  for (int b = gid; b < B; b += NG) {
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int row = side == 0 ? si[b] : sj[b];
+      if (side == 1 && row == si[b]) continue;
+      bool first = true;
+      for (int t = 0; t < b; ++t) first = first && (si[t] != row) && (sj[t] != row);
+      if (!first) continue;
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) {
+        const int c = (it * LPT + sub) * VEC;
+        if (c >= d) continue;
+        Frag<VEC> acc_i = frag_zero<VEC>(), acc_j = frag_zero<VEC>();
+        for (int t = b; t < B; ++t) {
+          const bool hi = si[t] == row, hj = sj[t] == row;
+          if (!hi && !hj) continue;
+          const float g = sg[t];
+          Frag<VEC> uu = ldg_frag<VEC>(U + (int64_t)su[t] * d + c);
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) {
+            const float gu = g * uu.v[kk];
+            if (hi) acc_i.v[kk] += gu;
+            if (hj) acc_j.v[kk] -= gu;
+          }
+        }
+        float* dst = gV + (int64_t)row * d + c;
+        Frag<VEC> cur = ld_frag<VEC>(dst);
+#pragma unroll
+        for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc_i.v[kk] + acc_j.v[kk];
+        st_frag<VEC>(dst, cur);
+      }
+    }
+  }
+}
+
+template <int VEC, int LPT, int NITER>
+struct DetSmallLauncher {
+  static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                 int B, int d, float inv_batch, float* gU, float* gV, float* loss, cudaStream_t st) {
+    k_det_small<VEC, LPT, NITER><<<1, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss);
+    MFCD_CHECK_LAUNCH();
+    return MFCD_OK;
+  }
+};
+
+static int launch_det_small(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                            int64_t start, int B, int d, float inv_batch, float* gU, float* gV, float* loss,
+                            cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(DetSmallLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, st);
+}
+
+}  // namespace mfcd
+
+// ---------------------------------------------------------------------------
+// large-batch deterministic path (sort + segmented reduction): segmented.cu
+// ---------------------------------------------------------------------------
+namespace mfcd {
+int launch_det_large(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                     int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
+                     float* loss, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t det_large_workspace_bytes(int64_t B, int d);
+
+// MODE 1 forward used by the large path: g_b -> gbuf, per-block loss partials
+template <int VEC, int LPT, int NITER>
+struct DetForwardLauncher {
+  static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                 int64_t B, int d, float inv_batch, float* gbuf, float* partials, int grid, cudaStream_t st) {
+    k_fwd_bwd<VEC, LPT, NITER, 1><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, nullptr,
+                                                            nullptr, gbuf, partials);
+    MFCD_CHECK_LAUNCH();
+    return MFCD_OK;
+  }
+};
+
+int launch_det_forward(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                       int64_t B, int d, float inv_batch, float* gbuf, float* partials, int grid, cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(DetForwardLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gbuf, partials, grid, st);
+}
+
+size_t det_workspace_bytes(int64_t B, int d) {
+  if (B <= kSmallB) return 0;
+  return det_large_workspace_bytes(B, d);
+}
+
+int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                       int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
+                       float* loss, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (B == 0) return MFCD_OK;
+  if (B <= kSmallB) return launch_det_small(U, V, rec, perm, start, (int)B, d, inv_batch, gU, gV, loss, st);
+  const size_t need = det_large_workspace_bytes(B, d);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("deterministic mode: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return MFCD_ERR_WORKSPACE;
+  }
+  return launch_det_large(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, ws, ws_bytes, st);
+}
+}  // namespace mfcd
+
+using namespace mfcd;
+
+static int check_common(const char* fn, const float* U, const float* V, const mfcd_triplet* rec, int64_t start,
+                        int64_t B, int d, float* gU, float* gV, float* loss) {
+  MFCD_REQUIRE(B >= 0 && start >= 0, "%s: negative size", fn);
+  MFCD_REQUIRE(d >= 1, "%s: d must be >= 1", fn);
+  if (B == 0) return MFCD_OK;
+  MFCD_REQUIRE(U && V && rec && gU && gV && loss, "%s: NULL pointer", fn);
+  MFCD_REQUIRE(B < (int64_t(1) << 31), "%s: batch too large", fn);
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_fwd_bwd(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                                    int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
+                                    float* loss, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, as_stream(stream));
+}
+
+extern "C" int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes) {
+  MFCD_REQUIRE(bytes != nullptr && B >= 0 && d >= 1, "mfcd_det_workspace_bytes: bad argument");
+  *bytes = det_workspace_bytes(B, d);
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec,
+                                        const int32_t* perm, int64_t start, int64_t B, int32_t d, float inv_batch,
+                                        int64_t n_users, int64_t n_items, float* gU, float* gV, float* loss,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd_det", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(n_users > 0 && n_items > 0, "mfcd_triplet_fwd_bwd_det: table sizes must be positive");
+  return launch_fwd_bwd_det(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, workspace,
+                            workspace_bytes, as_stream(stream));
+}
+
+// one epoch of structure.py:845-852 launched from C (no per-step python)
+extern "C" int mfcd_train_epoch(const mfcd_epoch_args* a) {
+  MFCD_REQUIRE(a != nullptr, "mfcd_train_epoch: args is NULL");
+  MFCD_REQUIRE(a->batch_size > 0 && a->n_samples >= 0 && a->d >= 1, "mfcd_train_epoch: bad sizes");
+  MFCD_REQUIRE(a->params && a->grads && a->rec && a->step_losses, "mfcd_train_epoch: NULL pointer");
+  MFCD_REQUIRE(a->optimizer == MFCD_OPT_ADAM || a->optimizer == MFCD_OPT_SGD, "mfcd_train_epoch: bad optimizer");
+  MFCD_REQUIRE(a->optimizer != MFCD_OPT_ADAM || (a->state1 && a->state2), "mfcd_train_epoch: Adam state is NULL");
+  cudaStream_t st = as_stream(a->stream);
+  const int64_t numel = (a->n_users + a->n_items) * a->d;
+  float* U = a->params;
+  float* V = a->params + a->n_users * a->d;
+  float* gU = a->grads;
+  float* gV = a->grads + a->n_users * a->d;
+  const int64_t n_steps = (a->n_samples + a->batch_size - 1) / a->batch_size;
+  if (n_steps == 0) return MFCD_OK;
+  MFCD_CUDA(cudaMemsetAsync(a->step_losses, 0, sizeof(float) * n_steps, st));
+  for (int64_t k = 0; k < n_steps; ++k) {
+    const int64_t start = k * a->batch_size;
+    const int64_t B = (a->n_samples - start) < a->batch_size ? (a->n_samples - start) : a->batch_size;
+    const float inv_b = 1.0f / (float)B;
+    int rc;
+    if (a->mode == MFCD_MODE_DETERMINISTIC)
+      rc = launch_fwd_bwd_det(U, V, a->rec, a->perm, start, B, a->d, inv_b, a->n_users, a->n_items, gU, gV,
+                              a->step_losses + k, a->workspace, a->workspace_bytes, st);
+    else
+      rc = launch_fwd_bwd_atomic(U, V, a->rec, a->perm, start, B, a->d, inv_b, gU, gV, a->step_losses + k, st);
+    if (rc != MFCD_OK) return rc;
+    const int64_t step = a->step0 + k + 1;
+    if (a->optimizer == MFCD_OPT_ADAM)
+      rc = launch_adam(a->params, a->grads, a->state1, a->state2, numel, a->lr, a->beta1, a->beta2, a->eps,
+                       a->weight_decay, step, 1, st);
+    else
+      rc = launch_sgd(a->params, a->grads, a->state1, numel, a->lr, a->momentum, a->weight_decay, step, 1, st);
+    if (rc != MFCD_OK) return rc;
+  }
+  return MFCD_OK;
+}

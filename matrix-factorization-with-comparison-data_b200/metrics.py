@@ -1,0 +1,184 @@
+"""Reconstruction / alignment / correlation metrics (kernels K5 and K6).
+
+Mirrors ``compute_reconstruction_error`` (structure.py:925-955) and
+``compute_alpha_and_norm_ratios`` (structure.py:958-1082).  The reference
+materialises UV^T, copies it to numpy and loops over rows in python; here one
+streaming pass (mfcd_recon_stats) leaves 6 fp64 sums per row, from which every
+scalar and per-row list is finished on the host in float64, and Spearman comes
+from GPU row ranks (mfcd_row_ranks + mfcd_row_pearson) over row blocks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, ptr, current_stream
+from .store import GroundTruth, compute_device
+
+
+def _row_stats(model, gt: GroundTruth, s: float):
+    fs = model.flat_state(gt.device)
+    dev = fs.params.device
+    n, m, d = fs.n, fs.m, fs.d
+    assert gt.shape == (n, m), f"X is {gt.shape}, model is {(n, m)}"
+    ubar = torch.empty(d, dtype=torch.float32, device=dev)
+    vbar = torch.empty(d, dtype=torch.float32, device=dev)
+    stats = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    xv = gt.xview()
+    with torch.cuda.device(dev):
+        st = current_stream()
+        check(lib.mfcd_table_col_means(ptr(fs.U), n, d, ptr(ubar), st), "mfcd_table_col_means(U)")
+        check(lib.mfcd_table_col_means(ptr(fs.V), m, d, ptr(vbar), st), "mfcd_table_col_means(V)")
+        check(lib.mfcd_recon_stats(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar), ptr(vbar),
+                                   ptr(stats), st), "mfcd_recon_stats")
+    return stats.cpu().numpy(), fs
+
+
+def compute_reconstruction_error(model, X, s):
+    """|| (UV^T - column means) - sX ||_F / || sX ||_F   (structure.py:939-955)."""
+    gt = GroundTruth.wrap(X)
+    st, _ = _row_stats(model, gt, s)
+    num = math.sqrt(float(st[:, 5].sum()))
+    den = abs(float(s)) * math.sqrt(float(st[:, 1].sum()))
+    return num / den
+
+
+def _centered_sums(st, m):
+    sx, sxx, sw, sww, sxw = st[:, 0], st[:, 1], st[:, 2], st[:, 3], st[:, 4]
+    cxx = np.maximum(sxx - sx * sx / m, 0.0)     # sum (x - xbar)^2
+    cww = np.maximum(sww - sw * sw / m, 0.0)     # sum (w - wbar)^2   (w already centred by <U_r, vbar>)
+    cxw = sxw - sx * sw / m                      # sum (x - xbar)(w - wbar)
+    return cxx, cww, cxw
+
+
+def _singular_values_lowrank(L, R):
+    """Singular values of L @ R.T for tall-skinny L (n x k), R (m x k) via two QRs."""
+    _, rl = torch.linalg.qr(L.double(), mode="r")
+    _, rr = torch.linalg.qr(R.double(), mode="r")
+    return torch.linalg.svdvals(rl @ rr.T)
+
+
+def _svd_error(fs, gt: GroundTruth, alpha, norm_X):
+    """|| alpha S(W_c) - S(X_c) ||_2 / (|| S(X_c) ||_2 + 1e-8)   (structure.py:1013-1017).
+    S(W_c): W_c = U (V - vbar)^T has rank <= d, so its singular values come from a
+    d x d core (library QR/SVD on tiny matrices); the remaining min(n,m)-d are 0.
+    S(X_c): low-rank X by the same trick, dense X by torch.linalg.svdvals (library)."""
+    n, m, d = fs.n, fs.m, fs.d
+    U = fs.U.view(n, d)
+    V = fs.V.view(m, d)
+    k = min(n, m)
+    s2 = _singular_values_lowrank(U, V - V.mean(dim=0, keepdim=True))
+    S2 = torch.zeros(k, dtype=torch.float64, device=U.device)
+    S2[: min(k, s2.numel())] = s2[:k]
+    if gt.X is None:
+        s1 = _singular_values_lowrank(gt.A * gt.scale, gt.B - gt.B.mean(dim=0, keepdim=True))
+        S1 = torch.zeros(k, dtype=torch.float64, device=U.device)
+        S1[: min(k, s1.numel())] = s1[:k]
+    else:
+        Xc = gt.X - gt.X.mean(dim=1, keepdim=True)
+        S1 = torch.linalg.svdvals(Xc).double()[:k]
+    diff = alpha * S2 - S1
+    return float(torch.linalg.norm(diff) / (torch.linalg.norm(S1) + 1e-8))
+
+
+def row_spearman(model, gt: GroundTruth, rows_mask=None, max_bytes=2 << 30):
+    """Spearman rho of every row of X against the same row of UV^T (float64
+    numpy array of length n; NaN where a row is constant)."""
+    fs = model.flat_state(gt.device)
+    dev = fs.params.device
+    n, m, d = fs.n, fs.m, fs.d
+    rho = torch.empty(n, dtype=torch.float64, device=dev)
+    per_row = 4 * m
+    one = C.c_size_t(0)
+    check(lib.mfcd_rank_workspace_bytes(1, m, C.byref(one)), "mfcd_rank_workspace_bytes")
+    chunk = int(max(1, min(n, max_bytes // (4 * per_row + max(one.value, 1)))))
+    ws_bytes = C.c_size_t(0)
+    check(lib.mfcd_rank_workspace_bytes(chunk, m, C.byref(ws_bytes)), "mfcd_rank_workspace_bytes")
+    ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+    wrows = torch.empty((chunk, m), dtype=torch.float32, device=dev)
+    rx = torch.empty((chunk, m), dtype=torch.float32, device=dev)
+    rw = torch.empty((chunk, m), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = current_stream()
+        for r0 in range(0, n, chunk):
+            nr = min(chunk, n - r0)
+            xrows = gt.rows(r0, nr).contiguous()
+            check(lib.mfcd_reconstruct_rows(ptr(fs.U), ptr(fs.V), r0, nr, m, d, ptr(wrows), st),
+                  "mfcd_reconstruct_rows")
+            check(lib.mfcd_row_ranks(ptr(xrows), nr, m, ptr(rx), ptr(ws), ws.numel(), st), "mfcd_row_ranks(X)")
+            check(lib.mfcd_row_ranks(ptr(wrows), nr, m, ptr(rw), ptr(ws), ws.numel(), st), "mfcd_row_ranks(W)")
+            check(lib.mfcd_row_pearson(ptr(rx), ptr(rw), nr, m, ptr(rho[r0:]), st), "mfcd_row_pearson")
+    return rho.cpu().numpy()
+
+
+def compute_alpha_and_norm_ratios(model, X_init):
+    """The reference's 14-tuple (structure.py:958-1082), same order and types:
+    alpha, norm_X, norm_ratio, reconstruction_error_scaled, pearson_mean, pearson_std,
+    spearman_mean, spearman_std, svd_error_scaled, slopes, correlations,
+    spearman_scores, reconstruction_error_scaled_per_row, alpha_per_row."""
+    gt = GroundTruth.wrap(X_init)
+    st, fs = _row_stats(model, gt, 1.0)
+    n, m = gt.shape
+    cxx, cww, cxw = _centered_sums(st, float(m))
+
+    dot = float(cxw.sum())
+    norm_w2 = float(cww.sum())
+    norm_w = math.sqrt(norm_w2)
+    norm_X = math.sqrt(float(cxx.sum()))
+    alpha = dot / (norm_w2 + 1e-8)
+    norm_ratio = norm_w / (norm_X + 1e-8)
+    rec_scaled = math.sqrt(max(alpha * alpha * norm_w2 - 2.0 * alpha * dot + norm_X * norm_X, 0.0)) / (norm_X + 1e-8)
+
+    std_x = np.sqrt(cxx / m)
+    std_w = np.sqrt(cww / m)
+    ok = (std_x > 1e-8) & (std_w > 1e-8)                       # structure.py:1006
+    with np.errstate(divide="ignore", invalid="ignore"):
+        corr_all = cxw / np.sqrt(cxx * cww)
+    correlations = [float(c) for c in corr_all[ok]]
+    pearson_mean = float(np.mean(correlations)) if correlations else 0.0
+
+    try:
+        svd_error_scaled = _svd_error(fs, gt, alpha, norm_X)
+    except Exception:                                          # the reference's bare except (:1018-1020)
+        pearson_mean = 0.0
+        svd_error_scaled = 1.0
+
+    spearman_scores = []
+    if ok.any():
+        rho = row_spearman(model, gt)
+        spearman_scores = [float(r) for r in rho[ok] if not math.isnan(r)]
+    spearman_mean = float(np.mean(spearman_scores)) if spearman_scores else 0.0
+    pearson_std = float(np.std(correlations)) if correlations else 0.0
+    spearman_std = float(np.std(spearman_scores)) if spearman_scores else 0.0
+
+    ok_slope = (cxx > 1e-8) & (std_w > 1e-8)                   # structure.py:1042-1043
+    with np.errstate(divide="ignore", invalid="ignore"):
+        slopes = [float(v) for v in (cxw / cxx)[ok_slope]]
+        alpha_rows = np.where(cww > 1e-8, cxw / np.where(cww > 1e-8, cww, 1.0), 0.0)   # :1057-1058
+    alpha_per_row = [float(a) for a in alpha_rows]
+    rec_row_sq = float((alpha_rows * alpha_rows * cww - 2.0 * alpha_rows * cxw + cxx).sum())
+    rec_row = math.sqrt(max(rec_row_sq, 0.0)) / (norm_X + 1e-8)
+
+    return (alpha, norm_X, norm_ratio, rec_scaled, pearson_mean, pearson_std, spearman_mean, spearman_std,
+            svd_error_scaled, slopes, correlations, spearman_scores, rec_row, alpha_per_row)
+
+
+def sampled_rows(model, X, row_indices):
+    """Rows of UV^T and of X for visual inspection (structure.py:388-392)."""
+    gt = GroundTruth.wrap(X)
+    fs = model.flat_state(gt.device)
+    dev = fs.params.device
+    n, m, d = fs.n, fs.m, fs.d
+    xs, ws = [], []
+    with torch.cuda.device(dev):
+        for r in row_indices:
+            r = int(r)
+            out = torch.empty((1, m), dtype=torch.float32, device=dev)
+            check(lib.mfcd_reconstruct_rows(ptr(fs.U), ptr(fs.V), r, 1, m, d, ptr(out), current_stream()),
+                  "mfcd_reconstruct_rows")
+            ws.append(out[0].cpu().numpy())
+            xs.append(gt.rows(r, 1)[0].cpu().numpy())
+    return np.stack(xs), np.stack(ws)

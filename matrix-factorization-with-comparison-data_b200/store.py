@@ -1,0 +1,215 @@
+"""Device-resident data for the hot path: ground-truth views, triplet records, loaders.
+
+Replaces the reference's python-side containers:
+  * the dense ``X`` tensor handed around by ``run_experiment`` (structure.py:353),
+  * ``BTLPreferenceDataset.data`` -- a python list of ``(u, i, j, label)`` tuples
+    (structure.py:507-519),
+  * the three ``DataLoader`` objects (structure.py:738-740).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, current_stream
+
+
+def compute_device(device=None) -> torch.device:
+    """The CUDA device the kernels run on.  The reference forwards ``device`` to
+    ``.to(device)``; here the compute device is always a GPU -- ``'cpu'`` only
+    says where user-visible tensors such as X live.  No GPU => loud failure."""
+    if not torch.cuda.is_available():
+        raise _lib.MfcdError("mfcd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is not None:
+        dev = torch.device(device)
+        if dev.type == "cuda":
+            return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
+
+
+class GroundTruth:
+    """X as the kernels see it (struct mfcd_xview): dense fp32 matrix, or the
+    low-rank product ``scale * A @ B.T`` evaluated on the fly (needed when the
+    dense matrix would not be worth materialising, e.g. 100k x 50k = 20 GB)."""
+
+    def __init__(self, X=None, A=None, B=None, scale=1.0, device=None):
+        dev = compute_device(device)
+        self.device = dev
+        if X is not None:
+            self.X = X.detach().to(dev, torch.float32).contiguous()
+            self.A = self.B = None
+            self.shape = tuple(self.X.shape)
+        else:
+            self.X = None
+            self.A = A.detach().to(dev, torch.float32).contiguous()
+            self.B = B.detach().to(dev, torch.float32).contiguous()
+            assert self.A.shape[1] == self.B.shape[1]
+            self.shape = (self.A.shape[0], self.B.shape[0])
+        self.scale = float(scale)
+
+    @classmethod
+    def wrap(cls, X, device=None):
+        return X if isinstance(X, GroundTruth) else cls(X=X, device=device)
+
+    def xview(self) -> _lib.XView:
+        v = _lib.XView()
+        if self.X is not None:
+            v.X, v.ldx, v.A, v.B, v.dx, v.scale = self.X.data_ptr(), self.X.stride(0), None, None, 0, 1.0
+        else:
+            v.X, v.ldx, v.A, v.B = None, 0, self.A.data_ptr(), self.B.data_ptr()
+            v.dx, v.scale = self.A.shape[1], self.scale
+        return v
+
+    def rows(self, r0, nr):
+        if self.X is not None:
+            return self.X[r0:r0 + nr]
+        out = torch.empty((nr, self.shape[1]), dtype=torch.float32, device=self.device)
+        xv = self.xview()
+        check(lib.mfcd_xview_rows(C.byref(xv), r0, nr, self.shape[1], ptr(out), current_stream()), "mfcd_xview_rows")
+        return out
+
+    def dense(self):
+        return self.X if self.X is not None else self.rows(0, self.shape[0])
+
+
+class TripletStore:
+    """N labelled comparisons as 16-byte records {int32 u, i, j; float z} in HBM."""
+
+    def __init__(self, rec: torch.Tensor):
+        assert rec.dtype == torch.int32 and rec.dim() == 2 and rec.shape[1] == 4 and rec.is_cuda
+        self.rec = rec.contiguous()
+
+    def __len__(self):
+        return self.rec.shape[0]
+
+    @property
+    def device(self):
+        return self.rec.device
+
+    @classmethod
+    def from_columns(cls, u, i, j, z, device=None):
+        """int64 u,i,j + float64 z columns (what the reference's collate yields) -> records."""
+        dev = compute_device(device)
+        cols = [torch.as_tensor(c) for c in (u, i, j)]
+        zc = torch.as_tensor(z)
+        N = cols[0].numel()
+        with torch.cuda.device(dev):
+            cu, ci, cj = [c.to(dev, torch.int64, non_blocking=True).contiguous() for c in cols]
+            cz = zc.to(dev, torch.float64, non_blocking=True).contiguous()
+            rec = torch.empty((N, 4), dtype=torch.int32, device=dev)
+            check(lib.mfcd_pack_triplets(ptr(cu), ptr(ci), ptr(cj), ptr(cz), N, ptr(rec), current_stream()),
+                  "mfcd_pack_triplets")
+        return cls(rec)
+
+    def columns(self):
+        """-> (u, i, j) int64 and z float64 device tensors, the reference's batch dtypes."""
+        N = len(self)
+        dev = self.device
+        with torch.cuda.device(dev):
+            u = torch.empty(N, dtype=torch.int64, device=dev)
+            i = torch.empty_like(u)
+            j = torch.empty_like(u)
+            z = torch.empty(N, dtype=torch.float64, device=dev)
+            check(lib.mfcd_unpack_triplets(ptr(self.rec), N, ptr(u), ptr(i), ptr(j), ptr(z), current_stream()),
+                  "mfcd_unpack_triplets")
+        return u, i, j, z
+
+    def slice(self, a, b):
+        return TripletStore(self.rec[a:b])
+
+
+class _DatasetView:
+    """Duck-type of BTLPreferenceDataset for code that pokes at ``loader.dataset``."""
+
+    def __init__(self, store: TripletStore):
+        self._store = store
+        self._data = None
+
+    def __len__(self):
+        return len(self._store)
+
+    @property
+    def data(self):
+        if self._data is None:
+            u, i, j, z = [c.cpu().tolist() for c in self._store.columns()]
+            self._data = list(zip(u, i, j, z))
+        return self._data
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+
+class TripletLoader:
+    """Stands in for ``DataLoader(BTLPreferenceDataset, batch_size, shuffle)``
+    (structure.py:738-740).  ``len()`` is the number of batches; iterating yields
+    ``(u, i, j, z)`` int64/int64/int64/float64 batches like default_collate does,
+    so reference-style consumers keep working, but the fast path never iterates:
+    it hands ``store.rec`` and an epoch permutation to the C ABI.
+
+    shuffle_rng:
+      "reference": the epoch order is drawn exactly like torch's RandomSampler
+                   does (a seed from the global CPU RNG, then randperm with that
+                   seed), so a seeded run visits the reference's batches;
+      "device":    randperm on the GPU (throughput runs).
+    """
+
+    def __init__(self, store: TripletStore, batch_size=64, shuffle=False, shuffle_rng="reference"):
+        self.store = store
+        self.batch_size = int(batch_size)
+        self.shuffle = bool(shuffle)
+        self.shuffle_rng = shuffle_rng
+        self.dataset = _DatasetView(store)
+
+    def __len__(self):
+        return (len(self.store) + self.batch_size - 1) // self.batch_size
+
+    def epoch_perm(self):
+        """int32 device permutation for one epoch, or None when not shuffling."""
+        if not self.shuffle:
+            return None
+        N = len(self.store)
+        if self.shuffle_rng == "reference":
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())     # RandomSampler.__iter__
+            g = torch.Generator()
+            g.manual_seed(seed)
+            perm = torch.randperm(N, generator=g)
+            return perm.to(self.store.device, torch.int32)
+        with torch.cuda.device(self.store.device):
+            return torch.randperm(N, device=self.store.device, dtype=torch.int32)
+
+    def __iter__(self):
+        u, i, j, z = self.store.columns()
+        perm = self.epoch_perm()
+        if perm is not None:
+            p = perm.long()
+            u, i, j, z = u[p], i[p], j[p], z[p]
+        for s in range(0, len(self.store), self.batch_size):
+            e = s + self.batch_size
+            yield u[s:e], i[s:e], j[s:e], z[s:e]
+
+
+def as_loader(loader, device=None) -> TripletLoader:
+    """Accept a TripletLoader, or a stock torch DataLoader over (u,i,j,z) rows
+    (materialised once into records)."""
+    if isinstance(loader, TripletLoader):
+        return loader
+    ds = getattr(loader, "dataset", None)
+    if ds is None:
+        raise TypeError(f"cannot use {type(loader).__name__} as a triplet loader")
+    rows = ds.data if hasattr(ds, "data") else [ds[k] for k in range(len(ds))]
+    if len(rows) == 0:
+        u = i = j = torch.empty(0, dtype=torch.int64)
+        z = torch.empty(0, dtype=torch.float64)
+    else:
+        u = torch.tensor([int(r[0]) for r in rows], dtype=torch.int64)
+        i = torch.tensor([int(r[1]) for r in rows], dtype=torch.int64)
+        j = torch.tensor([int(r[2]) for r in rows], dtype=torch.int64)
+        z = torch.tensor([float(r[3]) for r in rows], dtype=torch.float64)
+    store = TripletStore.from_columns(u, i, j, z, device=device)
+    sampler = getattr(loader, "sampler", None)
+    shuffle = type(sampler).__name__ == "RandomSampler"
+    return TripletLoader(store, batch_size=getattr(loader, "batch_size", 64) or 64, shuffle=shuffle)
