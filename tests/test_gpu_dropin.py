@@ -1,0 +1,86 @@
+"""End-to-end drop-in parity: structure.run_experiment / parameter_scan on the GPU path vs the reference's
+own run (golden train_c1.npz was recorded by running the reference's pipeline with the same seeds)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RESULT_KEYS = ["reconstruction_errors", "log_likelihoods", "accuracy", "gt_log_likelihoods", "gt_accuracy",
+               "train_losses", "val_losses", "alpha", "norm_X", "norm_ratio", "reconstruction_error_scaled",
+               "pearson_corr", "pearson_std", "spearman_corr", "spearman_std", "svd_error_scaled", "slopes",
+               "pearson_corr_matrix", "spearman_corr_matrix", "reconstruction_error_scaled_per_row", "alpha_per_row",
+               "sampled_UVT_rows", "sampled_X_rows"]
+
+
+def test_run_experiment_reference_mode_reproduces_the_reference(monkeypatch):
+    """Config 1 (100 x 100, d=2, p=0.1, s=1, K=1): seeded like the golden run, the whole pipeline
+    (X, triplets, split, labels, init, shuffles, training, metrics) must land on the reference's numbers."""
+    import structure
+    from mfcd_b200 import config
+    g = load_golden("train_c1.npz")
+    monkeypatch.setattr(config, "RNG_MODE", "reference")
+    torch.manual_seed(0); np.random.seed(0)
+    res = structure.run_experiment(100, 100, 2, 0.1, 1.0, "cpu", 1e-3, 1e-5, reps=1, num_epochs=3)
+    assert list(res.keys()) == RESULT_KEYS and all(len(v) == 1 for v in res.values())
+    rel = lambda a, b: np.abs(np.asarray(a, float) - np.asarray(b, float)).max() / np.abs(np.asarray(b, float)).max()
+    assert rel(res["train_losses"][0], g["train_losses"]) < 1e-5
+    assert rel(res["val_losses"][0], g["val_losses"]) < 1e-5
+    assert abs(res["accuracy"][0] - g["test_acc"]) < 1e-3 and abs(-res["log_likelihoods"][0] - g["test_loss"]) < 1e-5
+    assert abs(res["gt_accuracy"][0] - g["gt_acc"]) < 1e-3 and abs(-res["gt_log_likelihoods"][0] - g["gt_loss"]) < 1e-5
+    assert abs(res["reconstruction_errors"][0] - g["rec_err"]) < 1e-3 * g["rec_err"]
+    s = g["alpha_scalars"]
+    for key, ref in zip(["alpha", "norm_X", "norm_ratio", "reconstruction_error_scaled", "pearson_corr", "pearson_std",
+                         "spearman_corr", "spearman_std", "svd_error_scaled"], s[:9]):
+        assert abs(res[key][0] - ref) <= 1e-3 * max(abs(ref), 1e-3), (key, res[key][0], ref)
+    assert abs(res["reconstruction_error_scaled_per_row"][0] - s[9]) <= 1e-3 * abs(s[9])
+    assert isinstance(res["sampled_UVT_rows"][0], np.ndarray) and res["sampled_UVT_rows"][0].shape == (2, 100)
+    assert res["sampled_X_rows"][0].shape == (2, 100) and len(res["alpha_per_row"][0]) == 100
+
+
+@pytest.mark.parametrize("strategy", ["random", "margin", "popularity", "svd"])
+def test_run_experiment_device_mode_all_strategies(strategy):
+    """GPU samplers + GPU labels + GPU training: result-dict contract and sane learning signal."""
+    import structure
+    torch.manual_seed(3); np.random.seed(3)
+    res = structure.run_experiment(120, 90, 2, 0.5, 5.0, "cuda", 1e-2, 1e-5, reps=2, num_epochs=4, K=2,
+                                   strategy=strategy, soft_label=True)
+    assert list(res.keys()) == RESULT_KEYS and all(len(v) == 2 for v in res.values())
+    for rep in range(2):
+        tl = res["train_losses"][rep]
+        assert len(tl) == 4 and all(np.isfinite(tl)) and tl[-1] < tl[0]
+        assert 0.0 <= res["accuracy"][rep] <= 1.0 and 0.5 < res["gt_accuracy"][rep] <= 1.0
+        assert np.isfinite(res["reconstruction_errors"][rep]) and -1 <= res["spearman_corr"][rep] <= 1
+
+
+def test_parameter_scan_and_ground_truth_scan_run(tmp_path):
+    import structure
+    torch.manual_seed(0)
+    out = structure.parameter_scan(n=60, m=50, d=[2, 4], p=0.4, s=np.float64(2.0), device=torch.device("cuda"),
+                                   num_epochs=2, reps=1, K=2)
+    assert len(out) == 2 and out[1]["params"]["d"] == 4 and type(out[0]["params"]["s"]) is float
+    assert len(out[0]["results"]["train_losses"][0]) == 2
+    path = str(tmp_path / "d" / "r.pkl")
+    assert structure.parameter_scan(n=40, m=40, p=[0.3, 0.5], num_epochs=1, save_path=path, save_every=1) == []
+    import pickle
+    assert len(pickle.load(open(path, "rb"))) == 2
+    gt = structure.parameter_scan_ground_truth(n=60, m=50, p=[0.2, 0.4], d=2, s=5, device="cpu", K=[1, 3], reps=2)
+    assert len(gt) == 4 and len(gt[0]["results"]["gt_accuracy"]) == 2
+    assert all(0.5 < a <= 1.0 for r in gt for a in r["results"]["gt_accuracy"])
+
+
+def test_generate_x_device_mode_has_the_base_law():
+    """GPU 'base' generator: rank d, entries of std ~0.5, singular values sqrt(nm)/(2 sqrt d) (generation_data.py:359-369)."""
+    import structure
+    torch.manual_seed(0)
+    X = structure.generate_X(400, 300, 3, "cuda")
+    assert X.shape == (400, 300) and X.is_cuda
+    sv = torch.linalg.svdvals(X.double())
+    expect = np.sqrt(400 * 300) / (2 * np.sqrt(3))
+    assert torch.allclose(sv[:3], torch.full((3,), expect, dtype=torch.float64, device=X.device), rtol=1e-4)
+    assert sv[3] < 1e-3 * expect and abs(X.std().item() - 0.5) < 0.02
+    from generation_data import generate_low_rank_gpu
+    gt = generate_low_rank_gpu(400, 300, 3, "cuda", seed=5, force_factored=True)
+    assert gt.shape == (400, 300) and abs(gt.dense().std().item() - 0.5) < 0.02

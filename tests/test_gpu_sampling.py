@@ -1,0 +1,220 @@
+"""GPU tests for the samplers (K7), the dedup, the label sampler (K8) and the drop-in data path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mfcd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+# -- an independent Philox4x32-10 in numpy (Salmon et al.), to pin the device generator -------------
+def philox_np(seed, counter, stream):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [counter & 0xFFFFFFFF, (counter >> 32) & 0xFFFFFFFF, stream, 0]
+    k = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vector: counter = 0, key = 0
+    assert philox_np(0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_device_philox_matches_numpy(G):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    out = torch.empty(64, dtype=torch.float32, device=G.DEV)
+    seed, w0 = 0x1234567890ABCDEF, 1000
+    check(lib.mfcd_philox_uniforms(seed, w0, 64, ptr(out), current_stream()), "philox")
+    ref = [(philox_np(seed, (w0 + k) >> 2, 0x4C41424C)[(w0 + k) & 3] & 0xFFFFFF) / 16777216.0 for k in range(64)]
+    assert np.array_equal(out.cpu().numpy(), np.array(ref, np.float32))
+
+
+def _decode(keys, m):
+    k = keys.cpu().numpy().astype(np.uint64)
+    j = k % m; t = k // m
+    return np.stack([t // m, t % m, j], 1).astype(np.int64)
+
+
+def test_random_candidates_are_a_pure_function_of_the_counter(G):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    n, m, cnt = 1000, 77, 5000
+    a = torch.empty(cnt, dtype=torch.int64, device=G.DEV); b = torch.empty(cnt, dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_sample_random(n, m, cnt, 99, 0, ptr(a), current_stream()), "s")
+    check(lib.mfcd_sample_random(n, m, cnt - 100, 99, 100, ptr(b), current_stream()), "s")
+    assert torch.equal(a[100:], b[:cnt - 100])
+    # first candidates vs the numpy generator
+    for c in range(5):
+        r = philox_np(99, c, 0)
+        u, i, j = (r[0] * n) >> 32, (r[1] * m) >> 32, (r[2] * m) >> 32
+        key = a[c].item()
+        assert key == (-1 if i == j else (u * m + i) * m + j)
+    t = _decode(a[a != -1], m)
+    assert (t[:, 1] != t[:, 2]).all() and t[:, 0].max() < n and t[:, 1:].max() < m
+
+
+def test_unique_accept_equals_sequential_rule(G):
+    """mfcd_unique_accept == the reference's `if t not in exclude and t not in triplets` walk (oracle accept_stream)."""
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(1)
+    m = 6
+    cands = [(int(a), int(b), int(c)) for a, b, c in rng.integers(0, m, (4000, 3))]       # many duplicates, many i == j
+    exclude = {(int(a), int(b), int(c)) for a, b, c in rng.integers(0, m, (60, 3))}
+    want = 150
+    kept, _ = O.accept_stream(cands, want, exclude=exclude)
+    enc = lambda t: (t[0] * m + t[1]) * m + t[2]
+    keys = torch.tensor([(-1 if t[1] == t[2] else enc(t)) for t in cands], dtype=torch.int64, device=G.DEV)
+    seen = torch.tensor([enc(t) for t in exclude], dtype=torch.int64, device=G.DEV)
+    need = C.c_size_t(0)
+    check(lib.mfcd_unique_workspace_bytes(seen.numel(), keys.numel(), C.byref(need)), "ws")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=G.DEV)
+    out = torch.empty(want, dtype=torch.int64, device=G.DEV); n_out = torch.zeros(1, dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_unique_accept(ptr(seen), seen.numel(), ptr(keys), keys.numel(), want, ptr(out), ptr(n_out), ptr(ws),
+                                 need.value, current_stream()), "uniq")
+    got = int(n_out.item())
+    assert got == len(kept)
+    assert [tuple(r) for r in _decode(out[:got], m).tolist()] == kept
+    # asking for more than exist returns them all
+    kept_all, _ = O.accept_stream(cands, 10 ** 6, exclude=exclude)
+    out = torch.empty(len(cands), dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_unique_accept(ptr(seen), seen.numel(), ptr(keys), keys.numel(), len(cands), ptr(out), ptr(n_out), ptr(ws),
+                                 need.value, current_stream()), "uniq")
+    assert int(n_out.item()) == len(kept_all)
+
+
+@pytest.mark.parametrize("strategy", ["random", "margin", "popularity", "svd"])
+def test_sampler_predicates(G, strategy):
+    import structure
+    g = load_golden("samplers.npz")
+    X = torch.from_numpy(g["X"])
+    n, m = X.shape
+    torch.manual_seed(5)
+    num = {"random": 400, "margin": 300, "popularity": 200, "svd": 120}[strategy]
+    ts = structure.get_triplets_from_X(X, num, strategy=strategy)
+    t = np.array(ts.tolist(), np.int64)
+    assert len(ts) == num == len({tuple(r) for r in t.tolist()})
+    assert (t[:, 1] != t[:, 2]).all() and t.min() >= 0 and t[:, 0].max() < n and t[:, 1:].max() < m
+    if strategy == "margin":
+        thr = O.margin_threshold(g["X"], num)
+        assert all(abs(g["X"][u, i] - g["X"][u, j]) <= thr for u, i, j in t.tolist())
+    if strategy == "svd":
+        users, items, _, _ = O.svd_top_sets(g["X"], min(O.svd_rank(n, m, num), 3))
+        assert set(t[:, 0].tolist()) <= set(users.tolist())
+        assert set(t[:, 1:].ravel().tolist()) <= set(items.tolist())
+    # exclude is honoured and reseeding reproduces the draw
+    torch.manual_seed(6)
+    more = structure.get_triplets_from_X(X, 50, strategy=strategy, exclude=ts)
+    assert not ({tuple(r) for r in more.tolist()} & {tuple(r) for r in t.tolist()})
+    torch.manual_seed(5)
+    again = structure.get_triplets_from_X(X, num, strategy=strategy)
+    assert torch.equal(again.keys, ts.keys)
+    assert (int(t[0][0]), int(t[0][1]), int(t[0][2])) in ts and (n + 5, 0, 1) not in ts
+
+
+def test_svd_rank_errors_like_svds(G):
+    import structure
+    X = torch.zeros(40, 30)
+    with pytest.raises(ValueError):
+        structure.get_triplets_from_X(X, 5, strategy="svd")          # rank formula gives 0
+
+
+def test_popularity_marginals(G):
+    """chi-square of the first item against the zipf law; second item is the law without the first."""
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    from mfcd_b200 import sampling
+    n, m, cnt = 1000, 20, 400_000
+    cdf = torch.from_numpy(sampling.popularity_cdf(m, "zipf", 1.5)).to(G.DEV)
+    keys = torch.empty(cnt, dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_sample_popularity(n, m, cnt, 7, 0, ptr(cdf), ptr(keys), current_stream()), "pop")
+    assert (keys != -1).all()
+    t = _decode(keys, m)
+    p = O.popularity_probs(m, "zipf", 1.5)
+    obs = np.bincount(t[:, 1], minlength=m)
+    chi2 = ((obs - cnt * p) ** 2 / (cnt * p)).sum()
+    assert chi2 < 60                                               # 19 dof: 99.99% quantile ~ 52
+    sel = t[t[:, 1] == 0][:, 2]
+    p2 = p.copy(); p2[0] = 0; p2 /= p2.sum()
+    obs2 = np.bincount(sel, minlength=m)
+    chi2 = ((obs2[1:] - len(sel) * p2[1:]) ** 2 / (len(sel) * p2[1:])).sum()
+    assert obs2[0] == 0 and chi2 < 60
+    assert abs(np.bincount(t[:, 0], minlength=n).std() / (cnt / n) - np.sqrt(n / cnt)) < 0.02
+
+
+def test_label_replay_and_layout(G):
+    """same uniforms => the oracle's labels, bit for bit; hard = K consecutive copies, soft = mean of K draws."""
+    from mfcd_b200 import sampling
+    g = load_golden("samplers.npz")
+    X = g["X"]
+    n, m = X.shape
+    rng = np.random.default_rng(4)
+    t = np.unique(np.stack([rng.integers(0, n, 300), rng.integers(0, m, 300), rng.integers(0, m, 300)], 1), axis=0)
+    t = t[t[:, 1] != t[:, 2]]
+    keys = torch.from_numpy((t[:, 0] * m + t[:, 1]) * m + t[:, 2]).to(G.DEV)
+    ts = sampling.TripletSet(keys, n, m)
+    K, scale = 3, 2.5
+    uni = rng.random(len(t) * K).astype(np.float32)
+    q = O.btl_probability(X, t[:, 0], t[:, 1], t[:, 2], scale)
+    for soft in (False, True):
+        st = sampling.btl_records(torch.from_numpy(X), ts, scale=scale, K=K, soft=soft, uniforms=uni)
+        u, i, j, z = [c.cpu().numpy() for c in st.columns()]
+        ref = O.btl_labels_from_uniforms(q, uni, K, soft)
+        # q is recomputed on device (expf vs numpy exp): a uniform within 1 ulp of q could flip; none here
+        assert np.array_equal(z.astype(np.float32), ref)
+        rep = 1 if soft else K
+        assert np.array_equal(u, np.repeat(t[:, 0], rep)) and np.array_equal(i, np.repeat(t[:, 1], rep))
+    # Philox path: empirical frequency tracks q
+    big = sampling.btl_records(torch.from_numpy(X), ts, scale=scale, K=64, soft=True, seed=11)
+    z = big.columns()[3].cpu().numpy()
+    assert np.abs(z - q).mean() < 0.06
+    again = sampling.btl_records(torch.from_numpy(X), ts, scale=scale, K=64, soft=True, seed=11)
+    assert torch.equal(again.rec, big.rec)
+
+
+def test_split_reference_mode_reproduces_the_reference(G, monkeypatch):
+    """RNG_MODE='reference': same triplets, same split, same labels as the reference under the same seed."""
+    import structure
+    from mfcd_b200 import config
+    g = load_golden("samplers.npz")
+    monkeypatch.setattr(config, "RNG_MODE", "reference")
+    X = torch.from_numpy(g["X"])
+    torch.manual_seed(21); np.random.seed(21)
+    tr, va, te = structure.split_dataset_from_triplets(X, 100, scale=2.0, K=3, soft_label=True)
+    for tag, ld in (("tr", tr), ("va", va), ("te", te)):
+        u, i, j, z = [c.cpu().numpy() for c in ld.store.columns()]
+        assert np.array_equal(u, g[f"split_{tag}_u"]) and np.array_equal(i, g[f"split_{tag}_i"])
+        assert np.array_equal(j, g[f"split_{tag}_j"]) and np.array_equal(z, g[f"split_{tag}_z"])
+    assert len(tr) == 2 and len(va) == 1 and len(te) == 8 and tr.shuffle and not te.shuffle
+    assert tr.dataset[0] == (int(g["split_tr_u"][0]), int(g["split_tr_i"][0]), int(g["split_tr_j"][0]), float(g["split_tr_z"][0]))
+
+
+def test_split_device_mode_contract(G):
+    import structure
+    g = load_golden("samplers.npz")
+    X = torch.from_numpy(g["X"])
+    torch.manual_seed(1)
+    tr, va, te = structure.split_dataset_from_triplets(X, 100, scale=2.0, K=3, soft_label=True)
+    assert len(tr.store) == 80 and len(va.store) == 30 and len(te.store) == 167 * 3
+    z = tr.store.columns()[3].cpu().numpy()
+    assert np.allclose(z * 3, np.round(z * 3))
+    zt = te.store.columns()[3].cpu().numpy()
+    assert set(np.unique(zt)) <= {0.0, 1.0}
+    allk = []
+    for ld in (tr, va, te):
+        u, i, j, _ = [c.cpu().numpy() for c in ld.store.columns()]
+        allk.append(np.unique((u * 30 + i) * 30 + j))
+    assert len(np.intersect1d(allk[0], allk[1])) == 0 and len(np.intersect1d(allk[0], allk[2])) == 0
+    batch = next(iter(va))
+    assert batch[0].dtype == torch.int64 and batch[3].dtype == torch.float64 and len(batch[0]) == 30

@@ -1,0 +1,333 @@
+"""GPU parity tests for the training hot path (K1, K2, K3, epoch runner), all
+through the C ABI, against the golden fixtures recorded from the reference and
+against the numpy oracle.  Tolerances: 1e-5 relative for per-step loss and
+updated U/V in deterministic mode (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, batches_from
+from oracle import mfcd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KAT_TAGS = ["dup", "sat", "soft", "d2", "d3", "d32", "d64", "d128", "single"]
+TRAIN_FIXTURES = ["train_c1.npz", "train_d10_k3.npz", "train_soft_d4.npz", "train_d64.npz"]
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("mode", ["atomic", "deterministic"])
+@pytest.mark.parametrize("tag", KAT_TAGS)
+def test_kat_forward_backward(G, tag, mode):
+    g = load_golden("kat_fwd_bwd.npz")
+    U, V = g[tag + "_U"], g[tag + "_V"]
+    store = G.store_from(g[tag + "_u"], g[tag + "_i"], g[tag + "_j"], g[tag + "_z"])
+    loss, gU, gV = G.fwd_bwd(U, V, store, mode=mode)
+    assert abs(loss - g[tag + "_loss"]) <= 1e-5 * abs(g[tag + "_loss"]) + 1e-7
+    assert G.rel(gU, g[tag + "_gU"]) < 1e-5
+    assert G.rel(gV, g[tag + "_gV"]) < 1e-5
+
+
+def test_scores_match_reference_forward(G):
+    from mfcd_b200.trainer import MatrixFactorization
+    g = load_golden("kat_fwd_bwd.npz")
+    for tag in ("sat", "soft", "d64", "d3"):
+        U, V = g[tag + "_U"], g[tag + "_V"]
+        model = MatrixFactorization(U.shape[0], V.shape[0], U.shape[1])
+        with torch.no_grad():
+            model.U.copy_(torch.from_numpy(U)); model.V.copy_(torch.from_numpy(V))
+        p = model(torch.from_numpy(g[tag + "_u"]), torch.from_numpy(g[tag + "_i"]), torch.from_numpy(g[tag + "_j"]))
+        assert G.rel(p.cpu().numpy(), g[tag + "_pred"]) < 2e-6
+    p_sat = g["sat_pred"]
+    assert (p_sat == 0).any() and (p_sat == 1).any()
+
+
+def test_empty_and_ragged_batches(G):
+    g = load_golden("kat_fwd_bwd.npz")
+    U, V = g["soft_U"], g["soft_V"]
+    store = G.store_from(g["soft_u"], g["soft_i"], g["soft_j"], g["soft_z"])
+    loss, gU, gV = G.fwd_bwd(U, V, store, B=0)
+    assert loss == 0.0 and not gU.any() and not gV.any()
+    # a sub-range [5, 5+13) equals the oracle on that slice
+    sl = slice(5, 18)
+    lo, gUo, gVo = O.loss_and_grads(U, V, g["soft_u"][sl], g["soft_i"][sl], g["soft_j"][sl], g["soft_z"][sl].astype(np.float32))
+    for mode in ("atomic", "deterministic"):
+        loss, gU, gV = G.fwd_bwd(U, V, store, start=5, B=13, mode=mode)
+        assert abs(loss - lo) < 1e-5 * abs(lo) and G.rel(gU, gUo) < 1e-5 and G.rel(gV, gVo) < 1e-5
+
+
+def _random_problem(rng, n, m, d, B, hot=False):
+    U = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    V = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    u = rng.integers(0, n, B)
+    if hot:   # zipf-like: a few very hot items -> long segments that straddle many chunks
+        pr = 1.0 / np.arange(1, m + 1) ** 1.5; pr /= pr.sum()
+        i = rng.choice(m, B, p=pr); j = rng.choice(m, B, p=pr)
+    else:
+        i = rng.integers(0, m, B); j = rng.integers(0, m, B)
+    z = rng.integers(0, 2, B).astype(np.float64)
+    return U, V, u, i, j, z
+
+
+@pytest.mark.parametrize("d", [2, 10, 64, 128, 256])
+@pytest.mark.parametrize("hot", [False, True])
+def test_large_batch_paths_against_oracle(G, d, hot):
+    """B > 256 takes the sort + segmented-reduction path; permuted access; both modes vs oracle."""
+    rng = np.random.default_rng(100 + d + hot)
+    n, m, B = 300, 200, 3000
+    U, V, u, i, j, z = _random_problem(rng, n, m, d, B, hot)
+    perm = rng.permutation(B)
+    store = G.store_from(u, i, j, z)
+    lo, gUo, gVo = O.loss_and_grads(U, V, u[perm], i[perm], j[perm], z[perm].astype(np.float32))
+    for mode in ("atomic", "deterministic"):
+        loss, gU, gV = G.fwd_bwd(U, V, store, mode=mode, perm=perm)
+        assert abs(loss - lo) < 2e-5 * abs(lo), (mode, loss, lo)
+        assert G.rel(gU, gUo) < 2e-5 and G.rel(gV, gVo) < 2e-5, mode
+
+
+def test_deterministic_mode_is_bit_reproducible(G):
+    rng = np.random.default_rng(7)
+    U, V, u, i, j, z = _random_problem(rng, 500, 64, 64, 20000, hot=True)
+    store = G.store_from(u, i, j, z)
+    a = G.fwd_bwd(U, V, store, mode="deterministic")
+    b = G.fwd_bwd(U, V, store, mode="deterministic")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    c = G.fwd_bwd(U, V, store, mode="atomic")
+    assert G.rel(c[1], a[1]) < 1e-4 and G.rel(c[2], a[2]) < 1e-4 and abs(c[0] - a[0]) < 1e-5 * abs(a[0])
+
+
+def test_gradients_accumulate_and_scale(G):
+    """inv_batch is the global-batch scale (data parallel): two half batches with 1/B add up to the full batch."""
+    rng = np.random.default_rng(9)
+    U, V, u, i, j, z = _random_problem(rng, 50, 40, 16, 600)
+    store = G.store_from(u, i, j, z)
+    full = G.fwd_bwd(U, V, store, mode="deterministic")
+    for mode in ("atomic", "deterministic"):
+        l1, gU1, gV1 = G.fwd_bwd(U, V, store, start=0, B=300, mode=mode, inv_batch=1 / 600)
+        l2, gU2, gV2 = G.fwd_bwd(U, V, store, start=300, B=300, mode=mode, inv_batch=1 / 600, gU=gU1, gV=gV1)
+        assert abs(l1 + l2 - full[0]) < 1e-5 * abs(full[0])
+        assert G.rel(gU2, full[1]) < 1e-5 and G.rel(gV2, full[2]) < 1e-5
+
+
+def _adam_gpu(G, p, g, m, v, step, lr, wd, zero=1):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    pd, gd, md, vd = G.dev_f32(p), G.dev_f32(g), G.dev_f32(m), G.dev_f32(v)
+    check(lib.mfcd_adam_update(ptr(pd), ptr(gd), ptr(md), ptr(vd), pd.numel(), lr, 0.9, 0.999, 1e-8, wd, step, zero,
+                               current_stream()), "adam")
+    return pd.cpu().numpy(), gd.cpu().numpy(), md.cpu().numpy(), vd.cpu().numpy()
+
+
+@pytest.mark.parametrize("numel", [1, 7, 4096, 100003])
+def test_adam_kernel_matches_oracle(G, numel):
+    rng = np.random.default_rng(numel)
+    p = rng.standard_normal(numel).astype(np.float32)
+    g = (rng.standard_normal(numel) * 1e-2).astype(np.float32)
+    m = (rng.standard_normal(numel) * 1e-3).astype(np.float32)
+    v = (rng.random(numel) * 1e-5).astype(np.float32)
+    for step, wd in ((1, 0.0), (3, 1e-5), (1000, 1e-2)):
+        po, mo, vo = O.adam_step(p.copy(), g.copy(), m.copy(), v.copy(), step, lr=1e-3, weight_decay=wd)
+        pg, gg, mg, vg = _adam_gpu(G, p, g, m, v, step, 1e-3, wd)
+        assert G.rel(pg, po) < 1e-6 and G.rel(mg, mo) < 1e-6 and G.rel(vg, vo) < 1e-6
+        assert not gg.any()                                   # zero_grad fused
+    _, gkeep, _, _ = _adam_gpu(G, p, g, m, v, 1, 1e-3, 0.0, zero=0)
+    assert np.array_equal(gkeep, g)
+
+
+def test_adam_fixed_point(G):
+    """zero gradient, zero state, no weight decay: parameters must not move (idempotence)."""
+    p = np.linspace(-1, 1, 1001).astype(np.float32)
+    z = np.zeros_like(p)
+    pg, _, mg, vg = _adam_gpu(G, p, z, z, z, 1, 1e-3, 0.0)
+    assert np.array_equal(pg, p) and not mg.any() and not vg.any()
+
+
+def test_sgd_kernel_matches_oracle(G):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal(1000).astype(np.float32)
+    buf_o = np.zeros_like(p); pd = G.dev_f32(p); bd = G.dev_f32(buf_o); po = p.copy()
+    for step in (1, 2, 3):
+        g = rng.standard_normal(1000).astype(np.float32)
+        O.sgd_step(po, g.copy(), buf_o, step, lr=0.05, momentum=0.9, weight_decay=1e-4)
+        gd = G.dev_f32(g)
+        check(lib.mfcd_sgd_update(ptr(pd), ptr(gd), ptr(bd), 1000, 0.05, 0.9, 1e-4, step, 1, current_stream()), "sgd")
+        assert G.rel(pd.cpu().numpy(), po) < 1e-6 and not gd.cpu().numpy().any()
+
+
+def _train_through_abi(G, g, mode, epochs=None):
+    """Replay the reference's recorded batches through mfcd_train_epoch."""
+    from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec, run_epoch, resolve_mode
+    n, m, d = int(g["n"]), int(g["m"]), int(g["d"])
+    model = MatrixFactorization(n, m, d)
+    with torch.no_grad():
+        model.U.copy_(torch.from_numpy(g["U0"])); model.V.copy_(torch.from_numpy(g["V0"]))
+    fs = model.flat_state(G.DEV)
+    spec = OptimizerSpec.adam(lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    spe = int(g["steps_per_epoch"])
+    epochs = int(g["epochs"]) if epochs is None else epochs
+    sizes = g["batch_sizes"]
+    losses = []
+    off = 0
+    for e in range(epochs):
+        cnt = int(sizes[e * spe:(e + 1) * spe].sum())
+        store = G.store_from(g["batch_u"][off:off + cnt], g["batch_i"][off:off + cnt], g["batch_j"][off:off + cnt],
+                             g["batch_z"][off:off + cnt])
+        off += cnt
+        losses += run_epoch(fs, store, None, 64, spec, resolve_mode(mode, 64)).cpu().tolist()
+    return model, np.array(losses)
+
+
+@pytest.mark.parametrize("mode", ["deterministic", "atomic"])
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_epoch_runner_matches_reference_steps(G, name, mode):
+    """per-step loss and final U, V vs the reference's own run: 1e-5 relative (deterministic mode bar);
+    the atomic mode is held to the same bar at these sizes."""
+    g = load_golden(name)
+    model, losses = _train_through_abi(G, g, mode)
+    assert G.rel(losses, g["step_losses"]) < 1e-5
+    assert G.rel(model.U.detach().cpu().numpy(), g["U1"]) < 1e-5
+    assert G.rel(model.V.detach().cpu().numpy(), g["V1"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_step_snapshots(G, name):
+    from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec, run_epoch
+    g = load_golden(name)
+    n, m, d = int(g["n"]), int(g["m"]), int(g["d"])
+    model = MatrixFactorization(n, m, d)
+    with torch.no_grad():
+        model.U.copy_(torch.from_numpy(g["U0"])); model.V.copy_(torch.from_numpy(g["V0"]))
+    fs = model.flat_state(G.DEV)
+    spec = OptimizerSpec.adam(lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    batches = batches_from(g)
+    done = 0
+    for k in (1, 2, 5):
+        for (u, i, j, z) in batches[done:k]:
+            run_epoch(fs, G.store_from(u, i, j, z), None, 64, spec, 1)
+        done = k
+        assert fs.step == k
+        assert G.rel(model.U.detach().cpu().numpy(), g[f"U_step{k}"]) < 1e-5
+        assert G.rel(model.V.detach().cpu().numpy(), g[f"V_step{k}"]) < 1e-5
+
+
+def test_train_model_api_with_recorded_order(G):
+    """structure.train_model on loaders: epoch losses (mean of batch means) and validation losses vs the reference.
+    The recorded epoch orders are injected through epoch_perm so the same batches are visited."""
+    import structure
+    from mfcd_b200.store import TripletLoader
+    g = load_golden("train_d10_k3.npz")
+    n, m, d = int(g["n"]), int(g["m"]), int(g["d"])
+    train_store = G.store_from(g["train_u"], g["train_i"], g["train_j"], g["train_z"])
+    val_store = G.store_from(g["val_u"], g["val_i"], g["val_j"], g["val_z"])
+    # recover each epoch's permutation of the train dataset from the recorded batches
+    key = lambda u, i, j, z: (u.astype(np.int64) * m + i) * m + j
+    spe, N = int(g["steps_per_epoch"]), len(g["train_u"])
+    perms = []
+    ds_rows = np.stack([g["train_u"], g["train_i"], g["train_j"], g["train_z"]], 1)
+    for e in range(int(g["epochs"])):
+        rows = np.stack([g["batch_u"][e * N:(e + 1) * N], g["batch_i"][e * N:(e + 1) * N],
+                         g["batch_j"][e * N:(e + 1) * N], g["batch_z"][e * N:(e + 1) * N]], 1)
+        # rows may repeat (K=3 copies, equal labels): match greedily
+        from collections import defaultdict
+        pos = defaultdict(list)
+        for idx, r in enumerate(map(tuple, ds_rows)):
+            pos[r].append(idx)
+        perms.append(np.array([pos[tuple(r)].pop() for r in rows], np.int64))
+
+    class RecordedLoader(TripletLoader):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._e = 0
+
+        def epoch_perm(self):
+            p = torch.from_numpy(perms[self._e]).to(self.store.device, torch.int32)
+            self._e += 1
+            return p
+
+    model = structure.MatrixFactorization(n, m, d)
+    with torch.no_grad():
+        model.U.copy_(torch.from_numpy(g["U0"])); model.V.copy_(torch.from_numpy(g["V0"]))
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    tl = RecordedLoader(train_store, 64, shuffle=True)
+    vl = TripletLoader(val_store, 64)
+    tr, va = structure.train_model(model, tl, vl, opt, "cpu", num_epochs=int(g["epochs"]))
+    assert G.rel(tr, g["train_losses"]) < 1e-5 and G.rel(va, g["val_losses"]) < 1e-5
+    assert G.rel(model.U.detach().cpu().numpy(), g["U1"]) < 1e-5
+    st = opt.state[model.U]
+    assert int(st["step"]) == spe * int(g["epochs"]) and st["exp_avg"].shape == (n, d)
+    # evaluation API
+    test_store = G.store_from(g["test_u"], g["test_i"], g["test_j"], g["test_z"])
+    loss, acc = structure.evaluate_model(model, TripletLoader(test_store, 64), "cpu")
+    assert abs(loss - g["test_loss"]) < 1e-5 * abs(g["test_loss"]) and abs(acc - g["test_acc"]) < 1e-9
+    gl, ga = structure.compute_ground_truth_metrics(TripletLoader(test_store, 64), torch.from_numpy(g["X"]), "cpu")
+    assert abs(gl - g["gt_loss"]) < 1e-5 and abs(ga - g["gt_acc"]) < 1e-9
+    with pytest.raises(ZeroDivisionError):
+        structure.train_model(model, tl.__class__(train_store, 64), TripletLoader(val_store.slice(0, 0), 64), opt, "cpu",
+                              num_epochs=1)
+
+
+def test_pack_unpack_gather_roundtrip(G):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(1)
+    N = 10007
+    u, i, j = rng.integers(0, 2 ** 31 - 1, N), rng.integers(0, 1000, N), rng.integers(0, 1000, N)
+    z = rng.integers(0, 5, N) / 4.0
+    store = G.store_from(u, i, j, z)
+    cu, ci, cj, cz = [c.cpu().numpy() for c in store.columns()]
+    assert np.array_equal(cu, u) and np.array_equal(ci, i) and np.array_equal(cj, j) and np.array_equal(cz, z)
+    perm = torch.randperm(N, device=G.DEV, dtype=torch.int32)
+    out = torch.empty_like(store.rec)
+    check(lib.mfcd_gather_triplets(ptr(store.rec), ptr(perm), N, ptr(out), current_stream()), "gather")
+    assert torch.equal(out, store.rec[perm.long()])
+    assert len(G.store_from([], [], [], [])) == 0
+
+
+# ---- properties at BASELINE.json's full table shape (config 4: 100k x 50k, d = 64) ------------------
+def test_full_size_properties_c4_shape(G):
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    n, m, d, B = 100_000, 50_000, 64, 1 << 20
+    gen = torch.Generator(device=G.DEV); gen.manual_seed(4)
+    U = torch.randn(n, d, generator=gen, device=G.DEV) / 8
+    V = torch.randn(m, d, generator=gen, device=G.DEV) / 8
+    rec = torch.empty((B, 4), dtype=torch.int32, device=G.DEV)
+    rec[:, 0] = torch.randint(0, n, (B,), generator=gen, device=G.DEV)
+    rec[:, 1] = torch.randint(0, m, (B,), generator=gen, device=G.DEV)
+    rec[:, 2] = torch.randint(0, m, (B,), generator=gen, device=G.DEV)
+    rec[:, 3] = torch.randint(0, 2, (B,), generator=gen, device=G.DEV).float().view(torch.int32)
+    outs = {}
+    for mode in ("atomic", "deterministic"):
+        gU = torch.zeros_like(U); gV = torch.zeros_like(V); loss = torch.zeros(1, device=G.DEV)
+        if mode == "atomic":
+            check(lib.mfcd_triplet_fwd_bwd(ptr(U), ptr(V), ptr(rec), None, 0, B, d, 1.0 / B, ptr(gU), ptr(gV), ptr(loss),
+                                           current_stream()), "k1")
+        else:
+            need = C.c_size_t(0)
+            check(lib.mfcd_det_workspace_bytes(B, d, C.byref(need)), "ws")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=G.DEV)
+            check(lib.mfcd_triplet_fwd_bwd_det(ptr(U), ptr(V), ptr(rec), None, 0, B, d, 1.0 / B, n, m, ptr(gU), ptr(gV),
+                                               ptr(loss), ptr(ws), need.value, current_stream()), "k1det")
+        outs[mode] = (gU, gV, loss.item())
+        # checksum of checksums: every triplet adds +g U_u to row i and -g U_u to row j => column sums of gV vanish
+        col = gV.double().sum(dim=0).abs().max().item()
+        assert col < 1e-6 * gV.double().abs().sum().item() / d + 1e-9
+    # the two scatter modes agree at full size
+    a, b = outs["atomic"], outs["deterministic"]
+    assert (a[0] - b[0]).abs().max().item() < 1e-4 * b[0].abs().max().item()
+    assert (a[1] - b[1]).abs().max().item() < 1e-4 * b[1].abs().max().item()
+    assert abs(a[2] - b[2]) < 1e-5 * abs(b[2])
+    # the loss equals the evaluation kernel's loss over the same records (one batch)
+    bl = torch.zeros(1, device=G.DEV); correct = torch.zeros(1, dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_triplet_eval(ptr(U), ptr(V), ptr(rec), B, d, B, ptr(bl), ptr(correct), current_stream()), "k4")
+    assert abs(bl.item() - b[2]) < 1e-4 * abs(b[2])
+    # linearity: gradients scale with inv_batch
+    gU2 = torch.zeros_like(U); gV2 = torch.zeros_like(V); l2 = torch.zeros(1, device=G.DEV)
+    check(lib.mfcd_triplet_fwd_bwd(ptr(U), ptr(V), ptr(rec), None, 0, B, d, 2.0 / B, ptr(gU2), ptr(gV2), ptr(l2),
+                                   current_stream()), "k1")
+    assert (gU2 - 2 * a[0]).abs().max().item() < 1e-4 * gU2.abs().max().item()

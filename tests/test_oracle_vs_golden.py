@@ -143,3 +143,22 @@ def test_accept_stream_and_labels():
     uni = np.array([0.1, 0.3, 0.2, 0.9, 0.7, 0.8], np.float32)
     assert O.btl_labels_from_uniforms(q, uni, 3, soft=False).tolist() == [1, 0, 1, 0, 1, 0]
     assert np.allclose(O.btl_labels_from_uniforms(q, uni, 3, soft=True), [2 / 3, 1 / 3])
+
+
+@pytest.mark.parametrize("name", TRAIN_FIXTURES)
+def test_torch_port_replays_the_reference_bit_for_bit(name):
+    """oracle/torch_port.py runs the same ATen ops as the reference: identical losses and weights."""
+    import torch
+    from oracle import torch_port as TP
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    model = TP.PortModel(torch.from_numpy(g["U0"]), torch.from_numpy(g["V0"]))
+    opt = TP.make_optimizer(model, float(g["lr"]), float(g["wd"]))
+    losses = [TP.train_step(model, opt, torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j), torch.from_numpy(z))
+              for (u, i, j, z) in batches_from(g)]
+    assert np.array_equal(np.array(losses), g["step_losses"])
+    assert np.array_equal(model.U.detach().numpy(), g["U1"]) and np.array_equal(model.V.detach().numpy(), g["V1"])
+    test = [tuple(torch.from_numpy(a) for a in b)
+            for b in O.split_batches(g["test_u"], g["test_i"], g["test_j"], g["test_z"], 64)]
+    loss, acc = TP.eval_batches(model, test)
+    assert loss == pytest.approx(float(g["test_loss"]), rel=1e-12) and acc == pytest.approx(float(g["test_acc"]), abs=1e-12)
