@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=16.0)
+    ap.add_argument("--no-hot", action="store_true", help="disable hot-row privatisation in the atomic kernel")
     return ap.parse_args()
 
 
@@ -192,7 +193,9 @@ def main():
     fs = model.flat_state(dev)
     spec = OptimizerSpec.adam(lr=1e-3, weight_decay=1e-5)
     mode = 0 if args.mode == "atomic" else 1
-    engine = mdist.CudaEngine(fs, store, None, spec, mode)
+    engine = mdist.CudaEngine(fs, store, None, spec, mode, use_hot=not args.no_hot)
+    hot = store.hot_items(m, d, B) if (mode == 0 and not args.no_hot) else None
+    hot_args = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
     plan = mdist.PartitionedPlan([shard] * world, B, rank)
     losses = torch.zeros(total_steps, dtype=torch.float32, device=dev)
     numel = (n + m) * d
@@ -208,9 +211,10 @@ def main():
         if ev is not None:
             ev[0].record()
         if mode == 0:
-            check(lib.mfcd_triplet_fwd_bwd(ptr(fs.params), ptr(fs.params[nU:]), ptr(rec if rec is not None else store.rec),
-                                           None, s, bl, d, 1.0 / bg, ptr(fs.grads), ptr(fs.grads[nU:]),
-                                           ptr(losses[k:k + 1]), current_stream()), "k1")
+            check(lib.mfcd_triplet_fwd_bwd_hot(ptr(fs.params), ptr(fs.params[nU:]),
+                                               ptr(rec if rec is not None else store.rec), None, s, bl, d, 1.0 / bg,
+                                               ptr(fs.grads), ptr(fs.grads[nU:]), ptr(losses[k:k + 1]), *hot_args,
+                                               current_stream()), "k1")
         else:
             if rec is not None:
                 engine.store = TripletStore(rec)
@@ -341,6 +345,7 @@ def main():
             "config": {"workload": cfg["workload"], "n_users": n, "n_items": m, "d": d, "batch_per_gpu": B,
                        "global_batch": B * world, "scatter_mode": args.mode, "optimizer": "adam(lr=1e-3, wd=1e-5)",
                        "item_distribution": cfg["dist"], "parallelism": f"dp{world}",
+                       "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
                        "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB) are L2-resident "
                                     "by design of the algorithm"},
             "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,

@@ -86,6 +86,17 @@ int mfcd_triplet_fwd_bwd(const float* U, const float* V, const mfcd_triplet* rec
                          int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
                          float* loss, void* stream);
 
+/* Same as mfcd_triplet_fwd_bwd with hot-row privatisation for skewed item popularity: the caller names
+ * up to mfcd_max_hot_items(d) item rows that receive a large share of the updates
+ * (item_slot[row] = slot index in [0, n_hot) or -1, n_items int8 entries; hot_items[slot] = row).  Their
+ * gradient rows are accumulated in per-warp shared-memory images and reach gV as one reduction per row
+ * and CTA instead of one per triplet.  Results equal mfcd_triplet_fwd_bwd up to fp32 summation order. */
+int mfcd_max_hot_items(int32_t d, int32_t* out);
+int mfcd_triplet_fwd_bwd_hot(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                             int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
+                             float* loss, const int8_t* item_slot, const int32_t* hot_items, int32_t n_hot,
+                             void* stream);
+
 /* ---- K1+K2: deterministic variant ------------------------------------------
  * Same contract, but run-to-run bit-reproducible: per-row gradient sums are
  * formed by sorting the batch by destination row (stable, so batch order is
@@ -140,6 +151,10 @@ typedef struct mfcd_epoch_args {
   void* workspace;
   size_t workspace_bytes;
   void* stream;
+  const int8_t* item_slot;   /* optional hot-row privatisation (atomic mode), see mfcd_triplet_fwd_bwd_hot */
+  const int32_t* hot_items;
+  int32_t n_hot;
+  int32_t reserved2;
 } mfcd_epoch_args;
 int mfcd_train_epoch(const mfcd_epoch_args* args);
 

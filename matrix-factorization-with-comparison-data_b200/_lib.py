@@ -39,6 +39,7 @@ class EpochArgs(C.Structure):
         ("weight_decay", C.c_float), ("momentum", C.c_float),
         ("step0", C.c_int64), ("step_losses", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+        ("item_slot", C.c_void_p), ("hot_items", C.c_void_p), ("n_hot", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "mfcd_unpack_triplets": [P, I64, P, P, P, P, P],
     "mfcd_gather_triplets": [P, P, I64, P, P],
     "mfcd_triplet_fwd_bwd": [P, P, P, P, I64, I64, I32, F32, P, P, P, P],
+    "mfcd_max_hot_items": [I32, C.POINTER(I32)],
+    "mfcd_triplet_fwd_bwd_hot": [P, P, P, P, I64, I64, I32, F32, P, P, P, P, P, I32, P],
     "mfcd_det_workspace_bytes": [I64, I32, C.POINTER(SZ)],
     "mfcd_triplet_fwd_bwd_det": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
     "mfcd_adam_update": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, I32, P],

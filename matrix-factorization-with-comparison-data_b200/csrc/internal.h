@@ -9,7 +9,9 @@ int launch_sgd(float* p, float* g, float* buf, int64_t numel, float lr, float mo
                int64_t step, int zero_grad, cudaStream_t st);
 int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                           int64_t start, int64_t B, int d, float inv_batch, float* gU, float* gV,
-                          float* loss, cudaStream_t st);
+                          float* loss, const int8_t* item_slot, const int32_t* hot_items, int n_hot,
+                          cudaStream_t st);
+int max_hot_rows(int d);
 int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                        int64_t start, int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items,
                        float* gU, float* gV, float* loss, void* ws, size_t ws_bytes, cudaStream_t st);

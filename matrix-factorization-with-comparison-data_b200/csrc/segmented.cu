@@ -24,6 +24,7 @@
 namespace mfcd {
 
 constexpr int kChunk = 32;
+constexpr int kLongSpan = 48;     // straddling runs longer than this many chunks get a whole CTA
 constexpr int kSegBlock = 256;
 constexpr int kMaxLossPartials = 4096;
 
@@ -33,7 +34,7 @@ int launch_det_forward(const float* U, const float* V, const mfcd_triplet* rec, 
 static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct DetLayout {
-  size_t gbuf, partials, keys_a, keys_b, vals_a, vals_b, meta, part_first, part_last, cub_temp, total;
+  size_t gbuf, partials, keys_a, keys_b, vals_a, vals_b, meta, part_first, part_last, longlist, cub_temp, total;
   size_t cub_bytes;
 };
 
@@ -50,6 +51,8 @@ static DetLayout det_layout(int64_t B, int d) {
   L.meta = off;       off += align_up(sizeof(int4) * (B + 1));
   L.part_first = off; off += align_up(sizeof(float) * nchunks * d);
   L.part_last = off;  off += align_up(sizeof(float) * nchunks * d);
+  // long straddling runs (> kLongSpan chunks, each owning >= kLongSpan-1 chunks exclusively); [0] is the counter
+  L.longlist = off;   off += align_up(sizeof(int64_t) * (2 * (nchunks / (kLongSpan / 2) + 4) + 2));
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, B, 0, 32, (cudaStream_t)0);
@@ -170,10 +173,21 @@ k_seg_reduce(const float* __restrict__ T, const int4* __restrict__ meta, int64_t
   }
 }
 
+// last chunk that still belongs to the run of `key` which continues past chunk `ch`
+__device__ __forceinline__ int64_t run_last_chunk(const int4* __restrict__ meta, int64_t B, int64_t from, int key) {
+  int64_t lo = from, hi = B;                 // first position in [from, B) whose key differs (keys are sorted)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (meta[mid].x == key) lo = mid + 1; else hi = mid;
+  }
+  return (lo - 1) / kChunk;
+}
+
 template <int VEC, int LPT, int NITER>
 __global__ void __launch_bounds__(kSegBlock)
 k_seg_fixup(const int4* __restrict__ meta, int64_t B, int d, float* __restrict__ out,
-            const float* __restrict__ part_first, const float* __restrict__ part_last) {
+            const float* __restrict__ part_first, const float* __restrict__ part_last,
+            unsigned long long* __restrict__ longlist) {
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const int64_t group0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LPT;
@@ -188,19 +202,24 @@ k_seg_fixup(const int4* __restrict__ meta, int64_t B, int d, float* __restrict__
     const bool single = meta[s].x == key;
     const bool head_cont = (s > 0) && (meta[s - 1].x == meta[s].x);
     if (single && head_cont) continue;              // the run started in an earlier chunk
+    const int64_t last = run_last_chunk(meta, B, e, key);     // chunks ch+1 .. last hold a part_first row of this run
+    if (last - ch > kLongSpan) {                    // hot row: hand it to a whole CTA (k_seg_fixup_long)
+      if (sub == 0) {
+        const unsigned long long slot = atomicAdd(longlist, 1ull);
+        longlist[1 + 2 * slot] = (unsigned long long)ch;
+        longlist[2 + 2 * slot] = (unsigned long long)last;
+      }
+      continue;
+    }
 #pragma unroll
     for (int it = 0; it < NITER; ++it) {
       const int c = (it * LPT + sub) * VEC;
       if (c >= d) continue;
       Frag<VEC> tot = ld_frag<VEC>(part_last + ch * d + c);
-      for (int64_t c2 = ch + 1; c2 < nchunks; ++c2) {
+      for (int64_t c2 = ch + 1; c2 <= last; ++c2) {
         Frag<VEC> pf = ld_frag<VEC>(part_first + c2 * d + c);
 #pragma unroll
         for (int kk = 0; kk < VEC; ++kk) tot.v[kk] += pf.v[kk];
-        const int64_t s2 = c2 * kChunk;
-        const int64_t e2 = (s2 + kChunk < B) ? (s2 + kChunk) : B;
-        const bool goes_on = (meta[e2 - 1].x == key) && (e2 < B) && (meta[e2].x == key);
-        if (!goes_on) break;
       }
       float* dst = out + (int64_t)key * d + c;
       Frag<VEC> v = ld_frag<VEC>(dst);
@@ -211,24 +230,60 @@ k_seg_fixup(const int4* __restrict__ meta, int64_t B, int d, float* __restrict__
   }
 }
 
+// One CTA per long run: column sums of the contiguous block part_first[ch+1 .. last] in a fixed
+// order (row r is summed by row-lane r % RL sequentially, lanes combined in index order), plus part_last[ch].
+__global__ void __launch_bounds__(256)
+k_seg_fixup_long(const int4* __restrict__ meta, int d, float* __restrict__ out, const float* __restrict__ part_first,
+                 const float* __restrict__ part_last, const unsigned long long* __restrict__ longlist) {
+  extern __shared__ float s_part[];                 // [RL][d]
+  const unsigned long long count = longlist[0];
+  const int cols = d < 256 ? d : 256;               // columns handled per pass
+  const int RL = 256 / cols;                        // row lanes
+  for (unsigned long long w = blockIdx.x; w < count; w += gridDim.x) {
+    const int64_t ch = (int64_t)longlist[1 + 2 * w];
+    const int64_t last = (int64_t)longlist[2 + 2 * w];
+    const int key = meta[(ch + 1) * kChunk].x;
+    for (int c0 = 0; c0 < d; c0 += cols) {
+      const int c = c0 + (threadIdx.x % cols);
+      const int rl = threadIdx.x / cols;
+      float acc = 0.f;
+      if (rl < RL && c < d)
+        for (int64_t r = ch + 1 + rl; r <= last; r += RL) acc += part_first[r * d + c];
+      __syncthreads();
+      if (rl < RL && c < d) s_part[rl * cols + (c - c0)] = acc;
+      __syncthreads();
+      if (rl == 0 && c < d) {
+        float tot = part_last[ch * d + c];
+        for (int q = 0; q < RL; ++q) tot += s_part[q * cols + (c - c0)];
+        out[(int64_t)key * d + c] += tot;
+      }
+    }
+  }
+}
+
 template <int VEC, int LPT, int NITER>
 struct SegLauncher {
   static int run(bool side_u, const float* T, const int4* meta, int64_t B, int d, float* out, float* pf, float* pl,
-                 cudaStream_t st) {
+                 unsigned long long* longlist, cudaStream_t st) {
     const int64_t nchunks = (B + kChunk - 1) / kChunk;
     const int grid = grid_for(nchunks, kSegBlock / LPT, 8);
     if (side_u) k_seg_reduce<VEC, LPT, NITER, true><<<grid, kSegBlock, 0, st>>>(T, meta, B, d, out, pf, pl);
     else k_seg_reduce<VEC, LPT, NITER, false><<<grid, kSegBlock, 0, st>>>(T, meta, B, d, out, pf, pl);
     MFCD_CHECK_LAUNCH();
-    k_seg_fixup<VEC, LPT, NITER><<<grid, kSegBlock, 0, st>>>(meta, B, d, out, pf, pl);
+    MFCD_CUDA(cudaMemsetAsync(longlist, 0, sizeof(unsigned long long), st));
+    k_seg_fixup<VEC, LPT, NITER><<<grid, kSegBlock, 0, st>>>(meta, B, d, out, pf, pl, longlist);
+    MFCD_CHECK_LAUNCH();
+    const int long_grid = (int)((nchunks / kLongSpan + 1) < 512 ? (nchunks / kLongSpan + 1) : 512);
+    const int cols = d < 256 ? d : 256;
+    k_seg_fixup_long<<<long_grid, 256, sizeof(float) * (256 / cols) * cols, st>>>(meta, d, out, pf, pl, longlist);
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
 };
 
 static int launch_seg(bool side_u, const float* T, const int4* meta, int64_t B, int d, float* out, float* pf,
-                      float* pl, cudaStream_t st) {
-  MFCD_DISPATCH_ROW_SHAPE(SegLauncher, d, side_u, T, meta, B, d, out, pf, pl, st);
+                      float* pl, unsigned long long* longlist, cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(SegLauncher, d, side_u, T, meta, B, d, out, pf, pl, longlist, st);
 }
 
 static int bits_for(int64_t n) {
@@ -253,6 +308,7 @@ int launch_det_large(const float* U, const float* V, const mfcd_triplet* rec, co
   float* pf = reinterpret_cast<float*>(base + L.part_first);
   float* pl = reinterpret_cast<float*>(base + L.part_last);
   void* cub_temp = base + L.cub_temp;
+  unsigned long long* longlist = reinterpret_cast<unsigned long long*>(base + L.longlist);
 
   // forward with a FIXED grid so the loss partials reduce in a fixed order
   int grid = (int)((B + 255) / 256);
@@ -276,7 +332,7 @@ int launch_det_large(const float* U, const float* V, const mfcd_triplet* rec, co
     else if (side == 1) k_gather_meta<1><<<eg, 256, 0, st>>>(rec, perm, start, B, vals_b, gbuf, meta);
     else k_gather_meta<2><<<eg, 256, 0, st>>>(rec, perm, start, B, vals_b, gbuf, meta);
     MFCD_CHECK_LAUNCH();
-    rc = launch_seg(side == 0, side == 0 ? V : U, meta, B, d, side == 0 ? gU : gV, pf, pl, st);
+    rc = launch_seg(side == 0, side == 0 ? V : U, meta, B, d, side == 0 ? gU : gV, pf, pl, longlist, st);
     if (rc != MFCD_OK) return rc;
   }
   return MFCD_OK;

@@ -35,16 +35,56 @@ __device__ __forceinline__ float block_sum_256(float x, float* smem8) {
   return t;  // valid in warp 0
 }
 
+// Hot-row privatisation (HOT = true, atomic mode only).  Under popularity-biased
+// sampling a handful of item rows receive a large share of all gradient updates
+// (zipf 1.5: item 0 is in 38% of the pairs) and the L2 atomic unit serialises
+// same-line REDs at ~1 op/cycle, which caps the whole kernel.  The caller names
+// up to n_hot such rows (item_slot[row] = slot or -1); every warp keeps a private
+// fp32 accumulator image of those rows in shared memory, updates it with plain
+// LDS/STS (lane groups of one warp take turns, so there are no shared-memory
+// atomics), and the CTA flushes the 8 images as ONE reduction per row at the end.
+struct HotRows {
+  const int8_t* item_slot;   // [n_items] slot id or -1
+  const int32_t* hot_items;  // [n_hot] row id of each slot
+  int n_hot;
+};
+
+template <int VEC>
+__device__ __forceinline__ void smem_add_frag(float* p, const Frag<VEC>& f) {
+  Frag<VEC> cur;
+  if constexpr (VEC == 4) {
+    float4 t = *reinterpret_cast<float4*>(p);
+    t.x += f.v[0]; t.y += f.v[1]; t.z += f.v[2]; t.w += f.v[3];
+    *reinterpret_cast<float4*>(p) = t;
+  } else if constexpr (VEC == 2) {
+    float2 t = *reinterpret_cast<float2*>(p);
+    t.x += f.v[0]; t.y += f.v[1];
+    *reinterpret_cast<float2*>(p) = t;
+  } else {
+    *p += f.v[0];
+  }
+  (void)cur;
+}
+
 // MODE 0: atomic scatter into gU/gV.  MODE 1: write g_b to gbuf (deterministic path).
-template <int VEC, int LPT, int NITER, int MODE>
+template <int VEC, int LPT, int NITER, int MODE, bool HOT>
 __global__ void __launch_bounds__(kBlock)
 k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
           const int32_t* __restrict__ perm, int64_t start, int64_t B, int d, float inv_batch,
           float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ gbuf,
-          float* __restrict__ loss_out /* MODE 0: scalar accumulator; MODE 1: per-block partials */) {
+          float* __restrict__ loss_out /* MODE 0: scalar accumulator; MODE 1: per-block partials */,
+          HotRows hot) {
   constexpr int GPW = 32 / LPT;                                   // triplets side by side in a warp
   constexpr int UNR = (NITER > 1) ? 2 : (LPT >= 4 ? 4 : LPT);     // triplets in flight per group
   __shared__ float s_red[kBlock / 32];
+  extern __shared__ __align__(16) float s_hot[];                  // HOT: [8 warps][n_hot][d]
+  float* my_hot = nullptr;
+  if constexpr (HOT) {
+    const int per_warp = hot.n_hot * d;
+    for (int e = threadIdx.x; e < (kBlock / 32) * per_warp; e += kBlock) s_hot[e] = 0.f;
+    __syncthreads();
+    my_hot = s_hot + (threadIdx.x >> 5) * per_warp;
+  }
 
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
@@ -57,16 +97,19 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
   for (int64_t base = warp0 * 32; base < B; base += nwarps * 32) {
     const int64_t k = base + lane;
     int4 r = make_int4(0, 0, 0, 0);
+    int slots = 0xffff;                                            // (slot_i & 0xff) | (slot_j & 0xff) << 8, 0xff = cold
     if (k < B) {
       const int64_t idx = perm ? (int64_t)__ldg(perm + start + k) : (start + k);
       r = __ldg(reinterpret_cast<const int4*>(rec) + idx);
+      if constexpr (HOT)
+        slots = ((int)__ldg(hot.item_slot + r.y) & 0xff) | (((int)__ldg(hot.item_slot + r.z) & 0xff) << 8);
     }
     const int nvalid = (B - base) < 32 ? (int)(B - base) : 32;
 
 #pragma unroll 1
     for (int r0 = 0; r0 < LPT; r0 += UNR) {
       TripletRows<VEC, LPT, NITER> rows[UNR];
-      int tu[UNR], ti[UNR], tj[UNR];
+      int tu[UNR], ti[UNR], tj[UNR], ts[UNR];
       float tz[UNR];
       bool ok[UNR];
 #pragma unroll
@@ -76,6 +119,7 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
         ti[q] = __shfl_sync(0xffffffffu, r.y, e);
         tj[q] = __shfl_sync(0xffffffffu, r.z, e);
         tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+        ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
         ok[q] = e < nvalid;
         load_rows<VEC, LPT, NITER>(rows[q], U, V, tu[q], ti[q], tj[q], d, sub, ok[q]);
       }
@@ -104,13 +148,52 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
                   nb.v[kk] = -b.v[kk];
                 }
                 red_frag<VEC>(du + c, a);
-                red_frag<VEC>(di + c, b);
-                red_frag<VEC>(dj + c, nb);
+                if (!HOT || (ts[q] & 0xff) == 0xff) red_frag<VEC>(di + c, b);
+                if (!HOT || (ts[q] >> 8) == 0xff) red_frag<VEC>(dj + c, nb);
               }
             }
           }
         }
+        if constexpr (HOT && MODE == 0) {
+          // updates to privatised rows: lane groups of the warp take turns on the warp's own image
+          const bool mine = ok[q] && g != 0.f && ts[q] != 0xffff;
+          if (__any_sync(0xffffffffu, mine)) {
+#pragma unroll 1
+            for (int ph = 0; ph < GPW; ++ph) {
+              if (mine && grp == ph) {
+                const int si = ts[q] & 0xff, sj = ts[q] >> 8;
+#pragma unroll
+                for (int it = 0; it < NITER; ++it) {
+                  const int c = (it * LPT + sub) * VEC;
+                  if (c < d) {
+                    Frag<VEC> b, nb;
+#pragma unroll
+                    for (int kk = 0; kk < VEC; ++kk) {
+                      b.v[kk] = g * rows[q].uu[it].v[kk];
+                      nb.v[kk] = -b.v[kk];
+                    }
+                    if (si != 0xff) smem_add_frag<VEC>(my_hot + si * d + c, b);
+                    if (sj != 0xff) smem_add_frag<VEC>(my_hot + sj * d + c, nb);
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
       }
+    }
+  }
+
+  if constexpr (HOT && MODE == 0) {
+    // one reduction per privatised row and CTA
+    __syncthreads();
+    const int per_warp = hot.n_hot * d;
+    for (int e = threadIdx.x; e < per_warp; e += kBlock) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) t += s_hot[w * per_warp + e];
+      if (t != 0.f) atomicAdd(gV + (int64_t)__ldg(hot.hot_items + e / d) * d + (e % d), t);
     }
   }
 
@@ -124,20 +207,48 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
 template <int VEC, int LPT, int NITER>
 struct AtomicLauncher {
   static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
-                 int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss, cudaStream_t st) {
+                 int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss, HotRows hot,
+                 cudaStream_t st) {
+    if (hot.n_hot > 0) {
+      // privatised hot rows: dynamic smem = 8 warp images; taking turns needs <= 4 groups per warp
+      if constexpr (LPT >= 8) {
+        const size_t smem = sizeof(float) * (kBlock / 32) * (size_t)hot.n_hot * d;
+        auto kern = k_fwd_bwd<VEC, LPT, NITER, 0, true>;
+        if (smem > 48 * 1024)   // opt-in above the default limit (per device, so not cached)
+          MFCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = smem > 56 * 1024 ? 3 : 4;
+        const int grid = grid_for(B, kBlock * 8, per_sm);     // long-lived CTAs: few flushes per hot row
+        kern<<<grid, kBlock, smem, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, nullptr, loss, hot);
+        MFCD_CHECK_LAUNCH();
+        return MFCD_OK;
+      }
+    }
     const int grid = grid_for(B, kBlock, 4);           // a block pass covers 8 warp tiles of 32 triplets
-    k_fwd_bwd<VEC, LPT, NITER, 0><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV,
-                                                            nullptr, loss);
+    k_fwd_bwd<VEC, LPT, NITER, 0, false><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV,
+                                                                   nullptr, loss, HotRows{nullptr, nullptr, 0});
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
 };
 
+int max_hot_rows(int d) {
+  // 64 KB of shared memory for the 8 per-warp images; slots are int8 (<= 127)
+  RowShape s;
+  if (!row_shape_for(d, &s) || s.lpt < 8) return 0;
+  int h = (64 * 1024) / ((kBlock / 32) * d * (int)sizeof(float));
+  return h > 127 ? 127 : h;
+}
+
 int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                           int64_t start, int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss,
-                          cudaStream_t st) {
+                          const int8_t* item_slot, const int32_t* hot_items, int n_hot, cudaStream_t st) {
   if (B == 0) return MFCD_OK;
-  MFCD_DISPATCH_ROW_SHAPE(AtomicLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, st);
+  HotRows hot{item_slot, hot_items, (item_slot && hot_items) ? n_hot : 0};
+  if (hot.n_hot > max_hot_rows(d)) {
+    set_error("too many hot rows for d=%d: %d > %d", d, hot.n_hot, max_hot_rows(d));
+    return MFCD_ERR_ARG;
+  }
+  MFCD_DISPATCH_ROW_SHAPE(AtomicLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, hot, st);
 }
 
 // ===========================================================================
@@ -296,8 +407,8 @@ template <int VEC, int LPT, int NITER>
 struct DetForwardLauncher {
   static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
                  int64_t B, int d, float inv_batch, float* gbuf, float* partials, int grid, cudaStream_t st) {
-    k_fwd_bwd<VEC, LPT, NITER, 1><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, nullptr,
-                                                            nullptr, gbuf, partials);
+    k_fwd_bwd<VEC, LPT, NITER, 1, false><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, nullptr,
+                                                                   nullptr, gbuf, partials, HotRows{nullptr, nullptr, 0});
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
@@ -344,7 +455,25 @@ extern "C" int mfcd_triplet_fwd_bwd(const float* U, const float* V, const mfcd_t
                                     float* loss, void* stream) {
   int rc = check_common("mfcd_triplet_fwd_bwd", U, V, rec, start, B, d, gU, gV, loss);
   if (rc != MFCD_OK) return rc;
-  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, as_stream(stream));
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, nullptr, nullptr, 0,
+                               as_stream(stream));
+}
+
+extern "C" int mfcd_max_hot_items(int32_t d, int32_t* out) {
+  MFCD_REQUIRE(out != nullptr && d >= 1, "mfcd_max_hot_items: bad argument");
+  *out = max_hot_rows(d);
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_fwd_bwd_hot(const float* U, const float* V, const mfcd_triplet* rec,
+                                        const int32_t* perm, int64_t start, int64_t B, int32_t d, float inv_batch,
+                                        float* gU, float* gV, float* loss, const int8_t* item_slot,
+                                        const int32_t* hot_items, int32_t n_hot, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd_hot", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(n_hot >= 0, "mfcd_triplet_fwd_bwd_hot: n_hot < 0");
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot,
+                               as_stream(stream));
 }
 
 extern "C" int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes) {
@@ -389,7 +518,8 @@ extern "C" int mfcd_train_epoch(const mfcd_epoch_args* a) {
       rc = launch_fwd_bwd_det(U, V, a->rec, a->perm, start, B, a->d, inv_b, a->n_users, a->n_items, gU, gV,
                               a->step_losses + k, a->workspace, a->workspace_bytes, st);
     else
-      rc = launch_fwd_bwd_atomic(U, V, a->rec, a->perm, start, B, a->d, inv_b, gU, gV, a->step_losses + k, st);
+      rc = launch_fwd_bwd_atomic(U, V, a->rec, a->perm, start, B, a->d, inv_b, gU, gV, a->step_losses + k,
+                                 a->item_slot, a->hot_items, a->n_hot, st);
     if (rc != MFCD_OK) return rc;
     const int64_t step = a->step0 + k + 1;
     if (a->optimizer == MFCD_OPT_ADAM)

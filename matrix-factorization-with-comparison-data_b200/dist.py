@@ -86,8 +86,9 @@ class PartitionedPlan:
 class CudaEngine:
     """K1 / K3 on this rank's GPU through the C ABI."""
 
-    def __init__(self, flat_state, store, perm, spec, mode):
+    def __init__(self, flat_state, store, perm, spec, mode, use_hot=True):
         self.fs, self.store, self.perm, self.spec, self.mode = flat_state, store, perm, spec, mode
+        self.use_hot = use_hot
         self.ws = None
 
     def grads(self):
@@ -109,9 +110,12 @@ class CudaEngine:
                                                ws.numel() if ws is not None else 0, current_stream()),
                   "mfcd_triplet_fwd_bwd_det")
         else:
-            check(lib.mfcd_triplet_fwd_bwd(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec), ptr(self.perm),
-                                           start, b_local, fs.d, inv, ptr(fs.grads), ptr(fs.grads[nU:]),
-                                           ptr(loss_slot), current_stream()), "mfcd_triplet_fwd_bwd")
+            hot = self.store.hot_items(fs.m, fs.d, b_local) if self.use_hot else None
+            slot, items, n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
+            check(lib.mfcd_triplet_fwd_bwd_hot(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec),
+                                               ptr(self.perm), start, b_local, fs.d, inv, ptr(fs.grads),
+                                               ptr(fs.grads[nU:]), ptr(loss_slot), slot, items, n_hot,
+                                               current_stream()), "mfcd_triplet_fwd_bwd_hot")
 
     def update(self, a, b, step):
         fs, s = self.fs, self.spec

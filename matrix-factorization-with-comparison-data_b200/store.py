@@ -121,6 +121,33 @@ class TripletStore:
     def slice(self, a, b):
         return TripletStore(self.rec[a:b])
 
+    def hot_items(self, n_items, d, batch_size, min_hits_per_batch=2048, sample=1 << 24):
+        """Item rows that would each receive >= min_hits_per_batch gradient updates per batch
+        (popularity-biased sampling): candidates for K1's shared-memory privatisation.
+        Returns (item_slot int8[n_items], hot_items int32[H]) or None when the items are spread out.
+        Cached per (n_items, d, batch_size)."""
+        key = (int(n_items), int(d), int(batch_size))
+        cache = self.__dict__.setdefault("_hot_cache", {})
+        if key in cache:
+            return cache[key]
+        cap = C.c_int32(0)
+        check(lib.mfcd_max_hot_items(int(d), C.byref(cap)), "mfcd_max_hot_items")
+        out = None
+        N = len(self)
+        if cap.value > 0 and N > 0 and batch_size >= min_hits_per_batch:
+            rec = self.rec[: min(N, sample)]
+            counts = torch.bincount(rec[:, 1].long(), minlength=n_items) + torch.bincount(rec[:, 2].long(), minlength=n_items)
+            per_batch = counts.double() * (float(batch_size) / rec.shape[0])
+            k = min(cap.value, n_items)
+            top = torch.topk(per_batch, k)
+            sel = top.indices[top.values >= min_hits_per_batch]
+            if sel.numel() > 0:
+                slot = torch.full((n_items,), -1, dtype=torch.int8, device=self.device)
+                slot[sel] = torch.arange(sel.numel(), device=self.device).to(torch.int8)
+                out = (slot, sel.to(torch.int32).contiguous())
+        cache[key] = out
+        return out
+
 
 class _DatasetView:
     """Duck-type of BTLPreferenceDataset for code that pokes at ``loader.dataset``."""
@@ -157,18 +184,26 @@ class TripletLoader:
       "device":    randperm on the GPU (throughput runs).
     """
 
-    def __init__(self, store: TripletStore, batch_size=64, shuffle=False, shuffle_rng="reference"):
+    def __init__(self, store: TripletStore, batch_size=64, shuffle=False, shuffle_rng="reference",
+                 replay_iter_seed=None):
         self.store = store
         self.batch_size = int(batch_size)
         self.shuffle = bool(shuffle)
         self.shuffle_rng = shuffle_rng
+        # torch's DataLoader draws one int64 "base seed" from the global generator every time an
+        # iterator is created (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__), shuffled
+        # or not.  Replaying that draw keeps a seeded run on the reference's RNG stream.
+        self.replay_iter_seed = (shuffle_rng == "reference") if replay_iter_seed is None else bool(replay_iter_seed)
         self.dataset = _DatasetView(store)
 
     def __len__(self):
         return (len(self.store) + self.batch_size - 1) // self.batch_size
 
-    def epoch_perm(self):
-        """int32 device permutation for one epoch, or None when not shuffling."""
+    def begin_iteration(self):
+        """What `iter(DataLoader)` does to the global RNG, then the epoch order:
+        returns an int32 device permutation, or None when not shuffling."""
+        if self.replay_iter_seed:
+            torch.empty((), dtype=torch.int64).random_()                          # _base_seed
         if not self.shuffle:
             return None
         N = len(self.store)
@@ -180,6 +215,9 @@ class TripletLoader:
             return perm.to(self.store.device, torch.int32)
         with torch.cuda.device(self.store.device):
             return torch.randperm(N, device=self.store.device, dtype=torch.int32)
+
+    def epoch_perm(self):
+        return self.begin_iteration()
 
     def __iter__(self):
         u, i, j, z = self.store.columns()

@@ -209,6 +209,8 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     a.step0 = fs.step
     a.step_losses = ptr(losses)
     a.workspace, a.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
+    hot = store.hot_items(fs.m, fs.d, batch_size) if mode == MODE_ATOMIC else None
+    a.item_slot, a.hot_items, a.n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
     with torch.cuda.device(dev):
         a.stream = current_stream()
         check(lib.mfcd_train_epoch(C.byref(a)), "mfcd_train_epoch")
@@ -260,6 +262,7 @@ def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=1
     for _ in epochs:
         perm = train_loader.epoch_perm()
         step_losses = run_epoch(fs, train_loader.store, perm, train_loader.batch_size, spec, scatter)
+        val_loader.begin_iteration()
         vloss, _ = eval_batches(fs, val_loader.store, val_loader.batch_size)
         # one host sync per epoch
         train_losses.append(_sum_like_python(step_losses) / len(train_loader))
@@ -273,6 +276,7 @@ def evaluate_model(model, test_loader, device):
     dev = compute_device(device)
     loader = as_loader(test_loader, dev)
     fs = model.flat_state(dev)
+    loader.begin_iteration()
     batch_loss, correct = eval_batches(fs, loader.store, loader.batch_size)
     total = len(loader.store)
     accuracy = int(correct.item()) / total if total > 0 else 0.0
@@ -285,6 +289,7 @@ def compute_ground_truth_metrics(test_loader, X, device):
     dev = compute_device(device)
     loader = as_loader(test_loader, dev)
     gt = GroundTruth.wrap(X, dev)
+    loader.begin_iteration()
     N = len(loader.store)
     nb = len(loader)
     batch_mse = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)

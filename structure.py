@@ -360,8 +360,8 @@ def split_dataset_from_triplets(X, num_triplets, scale=1.0, K=1,
 
     rng = "reference" if _cfg.RNG_MODE == "reference" else "device"
     train_loader = TripletLoader(train_dataset.store, batch_size=batch_size, shuffle=True, shuffle_rng=rng)
-    val_loader = TripletLoader(val_dataset.store, batch_size=batch_size, shuffle=False)
-    test_loader = TripletLoader(test_dataset.store, batch_size=batch_size, shuffle=False)
+    val_loader = TripletLoader(val_dataset.store, batch_size=batch_size, shuffle=False, shuffle_rng=rng)
+    test_loader = TripletLoader(test_dataset.store, batch_size=batch_size, shuffle=False, shuffle_rng=rng)
     return train_loader, val_loader, test_loader
 
 

@@ -27,7 +27,7 @@ def fwd_bwd(U, V, store, start=0, B=None, mode="atomic", perm=None, inv_batch=No
     n, d = U.shape
     m = V.shape[0]
     B = len(store) - start if B is None else B
-    inv = (1.0 / B) if inv_batch is None else inv_batch
+    inv = (1.0 / max(B, 1)) if inv_batch is None else inv_batch
     Ud, Vd = dev_f32(U), dev_f32(V)
     gUd = torch.zeros_like(Ud) if gU is None else dev_f32(gU)
     gVd = torch.zeros_like(Vd) if gV is None else dev_f32(gV)

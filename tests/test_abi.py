@@ -54,7 +54,7 @@ def test_struct_layouts_match_the_header():
     from mfcd_b200 import _lib
     assert C.sizeof(_lib.XView) == 40           # ptr, i64, ptr, ptr, i32, f32
     assert _lib.EpochArgs.rec.offset == 64 and _lib.EpochArgs.step0.offset == 120
-    assert C.sizeof(_lib.EpochArgs) == 160
+    assert C.sizeof(_lib.EpochArgs) == 184 and _lib.EpochArgs.item_slot.offset == 160
 
 
 def test_argument_errors_are_reported_without_a_gpu():
