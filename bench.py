@@ -17,7 +17,6 @@ import ctypes as C
 import json
 import math
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -67,47 +66,56 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every
+    ~2 ms from a thread (the timed region is milliseconds long; nvidia-smi -lms would see 0-2 samples)."""
 
     def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
+        self.samples = []
+        self.reasons = 0
+        self.ok = False
+        self._stop = False
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:      # no NVML: report it rather than invent numbers
+            self.err = str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), float(mhz), int(r)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows[-3:]]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except Exception:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + self.err]}
+        self._stop = True
+        self.t.join(timeout=1.0)
+        nv = self.nv
+        inside = [(m, r) for (t, m, r) in self.samples if t0 <= t <= t1] or [(m, r) for (_, m, r) in self.samples[-2:]]
+        mhz = sorted(m for m, _ in inside)
+        bits = 0
+        for _, r in inside:
+            bits |= r
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        reasons = sorted(k for k, v in names.items() if bits & v)
+        return {"sm_mhz": (mhz[len(mhz) // 2] if mhz else None), "sm_max_mhz": self.max_mhz, "samples": len(inside),
+                "reasons": reasons}
 
 
 def reference_arm(args, cfg, rank):

@@ -99,10 +99,13 @@ __device__ __forceinline__ float partial_dot(const TripletRows<VEC, LPT, NITER>&
   return acc;
 }
 
+// Butterfly shuffles with offsets < LPT never leave a lane-aligned group, and every
+// caller runs them warp-convergently, so the constant full mask is correct -- and it
+// spares the MATCH.ANY / REDUX / VOTE mask validation ptxas emits for a variable mask.
 template <int LPT>
 __device__ __forceinline__ unsigned group_mask(int lane) {
-  if constexpr (LPT == 32) return 0xffffffffu;
-  else return ((1u << LPT) - 1u) << ((lane / LPT) * LPT);
+  (void)lane;
+  return 0xffffffffu;
 }
 
 }  // namespace mfcd

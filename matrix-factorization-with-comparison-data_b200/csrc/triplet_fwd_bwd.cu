@@ -14,6 +14,7 @@
 //
 // Algorithmic bytes per triplet: 16 (record) + 3*4*d (row reads) + 3*4*d
 // (gradient row updates) = 16 + 24 d.
+#include <stdlib.h>
 #include "internal.h"
 #include "shape_dispatch.cuh"
 
@@ -67,15 +68,22 @@ __device__ __forceinline__ void smem_add_frag(float* p, const Frag<VEC>& f) {
 }
 
 // MODE 0: atomic scatter into gU/gV.  MODE 1: write g_b to gbuf (deterministic path).
-template <int VEC, int LPT, int NITER, int MODE, bool HOT>
-__global__ void __launch_bounds__(kBlock)
+// VAR (tuning variant, env MFCD_K1_VARIANT): 2 (default) = 2 triplets in flight per lane group, 4 CTAs/SM
+// (56-62 registers); 0 = 4 in flight, 3 CTAs/SM (80 registers).  Measured on B200 at d=64, B=2^21:
+// var 2 is 8% faster with hot rows, equal on uniform items, 10% faster at d=32 (profiles/r01_notes.md).
+template <int NITER, int VAR, bool HOT>
+constexpr int k1_min_blocks() { return NITER > 2 ? 2 : (NITER == 2 ? 3 : (VAR == 0 ? 3 : 4)); }
+
+template <int VEC, int LPT, int NITER, int MODE, bool HOT, int VAR = 0>
+__global__ void __launch_bounds__(kBlock, k1_min_blocks<NITER, VAR, HOT>())
 k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
           const int32_t* __restrict__ perm, int64_t start, int64_t B, int d, float inv_batch,
           float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ gbuf,
           float* __restrict__ loss_out /* MODE 0: scalar accumulator; MODE 1: per-block partials */,
           HotRows hot) {
   constexpr int GPW = 32 / LPT;                                   // triplets side by side in a warp
-  constexpr int UNR = (NITER > 1) ? 2 : (LPT >= 4 ? 4 : LPT);     // triplets in flight per group
+  constexpr int UNR0 = (NITER > 1 || VAR == 2) ? 2 : 4;
+  constexpr int UNR = UNR0 < LPT ? UNR0 : LPT;                    // triplets in flight per group
   __shared__ float s_red[kBlock / 32];
   extern __shared__ __align__(16) float s_hot[];                  // HOT: [8 warps][n_hot][d]
   float* my_hot = nullptr;
@@ -209,23 +217,25 @@ struct AtomicLauncher {
   static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
                  int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss, HotRows hot,
                  cudaStream_t st) {
+    static const int var = getenv("MFCD_K1_VARIANT") ? atoi(getenv("MFCD_K1_VARIANT")) : 2;
     if (hot.n_hot > 0) {
       // privatised hot rows: dynamic smem = 8 warp images; taking turns needs <= 4 groups per warp
       if constexpr (LPT >= 8) {
         const size_t smem = sizeof(float) * (kBlock / 32) * (size_t)hot.n_hot * d;
-        auto kern = k_fwd_bwd<VEC, LPT, NITER, 0, true>;
-        if (smem > 48 * 1024)   // opt-in above the default limit (per device, so not cached)
+        auto kern = var == 2 ? k_fwd_bwd<VEC, LPT, NITER, 0, true, 2> : k_fwd_bwd<VEC, LPT, NITER, 0, true, 0>;
+        if (smem > 40 * 1024)   // opt-in above the default 48 KB (static + dynamic) limit; per device, so not cached
           MFCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = smem > 56 * 1024 ? 3 : 4;
+        const int per_sm = smem > 52 * 1024 ? 3 : 4;
         const int grid = grid_for(B, kBlock * 8, per_sm);     // long-lived CTAs: few flushes per hot row
         kern<<<grid, kBlock, smem, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, nullptr, loss, hot);
         MFCD_CHECK_LAUNCH();
         return MFCD_OK;
       }
     }
-    const int grid = grid_for(B, kBlock, 4);           // a block pass covers 8 warp tiles of 32 triplets
-    k_fwd_bwd<VEC, LPT, NITER, 0, false><<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV,
-                                                                   nullptr, loss, HotRows{nullptr, nullptr, 0});
+    auto kern = var == 2 ? k_fwd_bwd<VEC, LPT, NITER, 0, false, 2> : k_fwd_bwd<VEC, LPT, NITER, 0, false, 0>;
+    const int grid = grid_for(B, kBlock, var == 0 ? 3 : 4);   // a block pass covers 8 warp tiles of 32 triplets
+    kern<<<grid, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, nullptr, loss,
+                                  HotRows{nullptr, nullptr, 0});
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
@@ -235,7 +245,8 @@ int max_hot_rows(int d) {
   // 64 KB of shared memory for the 8 per-warp images; slots are int8 (<= 127)
   RowShape s;
   if (!row_shape_for(d, &s) || s.lpt < 8) return 0;
-  int h = (64 * 1024) / ((kBlock / 32) * d * (int)sizeof(float));
+  static const int budget_kb = getenv("MFCD_HOT_SMEM_KB") ? atoi(getenv("MFCD_HOT_SMEM_KB")) : 64;
+  int h = (budget_kb * 1024) / ((kBlock / 32) * d * (int)sizeof(float));
   return h > 127 ? 127 : h;
 }
 
