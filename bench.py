@@ -45,13 +45,19 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=1 << 21, help="triplets per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 22, help="triplets per GPU per step")
     ap.add_argument("--mode", default="atomic", choices=["atomic", "deterministic"])
     ap.add_argument("--cpu-batch", type=int, default=65536)
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = sized for ~15 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--bucket-mb", type=float, default=16.0)
+    ap.add_argument("--bucket-mb", type=float, default=0.0,
+                    help="gradient all-reduce bucket size; 0 = one all-reduce of the whole flat gradient "
+                         "(measured faster than 16 MB buckets on NVLink: profiles/r01_notes.md)")
+    ap.add_argument("--dp-backend", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory "
+                         "(K9); 'nccl' = NCCL all-reduce + K3")
+    ap.add_argument("--no-multimem", action="store_true")
     ap.add_argument("--no-hot", action="store_true", help="disable hot-row privatisation in the atomic kernel")
     return ap.parse_args()
 
@@ -198,7 +204,12 @@ def main():
 
     torch.manual_seed(7)                           # identical replicas on every rank
     model = MatrixFactorization(n, m, d)
-    fs = model.flat_state(dev)
+    exchange = None
+    if world > 1 and args.dp_backend == "peer":
+        exchange = mdist.PeerExchange((n + m) * d, dev, use_multimem=not args.no_multimem)
+        fs = model.flat_state(dev, storage=exchange.storage())
+    else:
+        fs = model.flat_state(dev)
     spec = OptimizerSpec.adam(lr=1e-3, weight_decay=1e-5)
     mode = 0 if args.mode == "atomic" else 1
     engine = mdist.CudaEngine(fs, store, None, spec, mode, use_hot=not args.no_hot)
@@ -207,7 +218,7 @@ def main():
     plan = mdist.PartitionedPlan([shard] * world, B, rank)
     losses = torch.zeros(total_steps, dtype=torch.float32, device=dev)
     numel = (n + m) * d
-    bucket_elems = int(args.bucket_mb * (1 << 20) / 4)
+    bucket_elems = int(args.bucket_mb * (1 << 20) / 4) if args.bucket_mb > 0 else numel
     n_buckets = len(mdist.bucket_bounds(numel, bucket_elems)) if world > 1 else 1
     nU = n * d
 
@@ -231,7 +242,12 @@ def main():
         if ev is not None:
             ev[1].record()
         g = fs.grads
-        if world > 1:
+        if exchange is not None:
+            exchange.step(fs, spec, fs.step + 1)
+        elif world > 1 and n_buckets == 1:
+            dist.all_reduce(g)
+            engine.update(0, numel, fs.step + 1)
+        elif world > 1:
             bounds = mdist.bucket_bounds(numel, bucket_elems)
             works = [dist.all_reduce(g[a:b], async_op=True) for a, b in bounds]
             for (a, b), w in zip(bounds, works):
@@ -348,11 +364,14 @@ def main():
                 traffic = None
         line = {
             "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "n_users": n, "n_items": m, "d": d, "batch_per_gpu": B,
                        "global_batch": B * world, "scatter_mode": args.mode, "optimizer": "adam(lr=1e-3, wd=1e-5)",
                        "item_distribution": cfg["dist"], "parallelism": f"dp{world}",
+                       "dp_exchange": ("none" if world == 1 else ("peer-memory fused K9" + (" (multimem)" if exchange.multimem else " (p2p)")
+                                                                  if exchange is not None else "nccl all-reduce + K3")),
                        "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
                        "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB) are L2-resident "
                                     "by design of the algorithm"},

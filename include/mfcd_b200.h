@@ -121,6 +121,23 @@ int mfcd_adam_update(float* p, float* g, float* m, float* v, int64_t numel, floa
 int mfcd_sgd_update(float* p, float* g, float* buf, int64_t numel, float lr, float momentum,
                     float weight_decay, int64_t step, int32_t zero_grad, void* stream);
 
+/* ---- K9: fused gradient exchange + Adam over NVLink peer memory (data parallel) -------------
+ * Replaces "all-reduce the flat gradient, then mfcd_adam_update on every rank" by one kernel per
+ * rank: rank r owns the slice mfcd_dp_shard_range(numel, r, world) of the flat parameter vector,
+ * sums that slice of the gradient over all ranks by reading the peers' gradient buffers directly
+ * (peer_grads[q] = address of rank q's buffer as mapped in THIS process; or, when mc_grads /
+ * mc_params are non-zero NVSwitch multicast addresses of the same buffers, one
+ * multimem.ld_reduce), applies Adam (m, v: this rank's full-size moment arrays, only the owned
+ * slice is touched) and writes the updated slice into every rank's parameter replica
+ * (peer_params[q], or one multimem.st).  peer_* are HOST arrays of `world` device addresses.
+ * The caller must (a) barrier across ranks before the call (all local gradients final) and
+ * after it (all replicas complete, all gradient reads done), (b) then clear its gradients. */
+int mfcd_dp_shard_range(int64_t numel, int32_t rank, int32_t world, int64_t* begin, int64_t* end);
+int mfcd_dp_fused_adam(const uint64_t* peer_grads, const uint64_t* peer_params, uint64_t mc_grads,
+                       uint64_t mc_params, int32_t rank, int32_t world, int64_t numel, float* m, float* v,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                       void* stream);
+
 /* ---- one training epoch, launched from C ------------------------------------
  * The inner loop of train_model (structure.py:845-852) for one epoch on one GPU:
  * for each batch k: K1 (atomic or deterministic) then K3, with the batch-mean

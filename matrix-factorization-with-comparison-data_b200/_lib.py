@@ -64,6 +64,9 @@ SIGNATURES = {
     "mfcd_triplet_fwd_bwd_det": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
     "mfcd_adam_update": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, I32, P],
     "mfcd_sgd_update": [P, P, P, I64, F32, F32, F32, I64, I32, P],
+    "mfcd_dp_shard_range": [I64, I32, I32, C.POINTER(I64), C.POINTER(I64)],
+    "mfcd_dp_fused_adam": [C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32, F32, F32, F32, F32,
+                           I64, P],
     "mfcd_train_epoch": [C.POINTER(EpochArgs)],
     "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P],
     "mfcd_ground_truth_eval": [C.POINTER(XView), P, I64, I64, P, P, P],

@@ -55,15 +55,16 @@ class MatrixFactorization(nn.Module):
         self._flat = None
 
     # -- flat CUDA storage ---------------------------------------------------
-    def flat_state(self, device=None):
+    def flat_state(self, device=None, storage=None):
+        """storage = (params, grads): externally allocated flat fp32 CUDA buffers to live in."""
         n, d = self.U.shape
         m = self.V.shape[0]
         fs = self._flat
-        if (fs is not None and fs.params.is_cuda and self.U.data_ptr() == fs.params.data_ptr()
+        if (storage is None and fs is not None and fs.params.is_cuda and self.U.data_ptr() == fs.params.data_ptr()
                 and self.V.data_ptr() == fs.params.data_ptr() + 4 * n * d):
             return fs
         dev = compute_device(device if device is not None else (self.U.device if self.U.is_cuda else None))
-        fs = _FlatState(n, m, d, dev)
+        fs = _FlatState(n, m, d, dev, *(storage or ()))
         with torch.no_grad():
             fs.params[: n * d].view(n, d).copy_(self.U.detach())
             fs.params[n * d:].view(m, d).copy_(self.V.detach())
@@ -90,11 +91,12 @@ class MatrixFactorization(nn.Module):
 class _FlatState:
     """(n+m)*d fp32 parameters, gradients and two optimiser moments, U first."""
 
-    def __init__(self, n, m, d, device):
+    def __init__(self, n, m, d, device, params=None, grads=None):
         self.n, self.m, self.d = n, m, d
         numel = (n + m) * d
-        self.params = torch.zeros(numel, dtype=torch.float32, device=device)
-        self.grads = torch.zeros(numel, dtype=torch.float32, device=device)
+        # params / grads may be handed in (symmetric-memory buffers shared with peer GPUs, dist.PeerExchange)
+        self.params = torch.zeros(numel, dtype=torch.float32, device=device) if params is None else params[:numel]
+        self.grads = torch.zeros(numel, dtype=torch.float32, device=device) if grads is None else grads[:numel]
         self.state1 = torch.zeros(numel, dtype=torch.float32, device=device)
         self.state2 = torch.zeros(numel, dtype=torch.float32, device=device)
         self.step = 0
