@@ -267,8 +267,9 @@ def main():
         one_step(k)
     k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local_rank) if rank == 0 else None     # NVML init happens BEFORE the barrier (it takes ms)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     wall0 = time.perf_counter()
     t_begin.record()
     for k in range(K):
