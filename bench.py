@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--dp-backend", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory "
                          "(K9); 'nccl' = NCCL all-reduce + K3")
-    ap.add_argument("--no-multimem", action="store_true")
+    ap.add_argument("--multimem", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--no-hot", action="store_true", help="disable hot-row privatisation in the atomic kernel")
     return ap.parse_args()
 
@@ -206,7 +206,8 @@ def main():
     model = MatrixFactorization(n, m, d)
     exchange = None
     if world > 1 and args.dp_backend == "peer":
-        exchange = mdist.PeerExchange((n + m) * d, dev, use_multimem=not args.no_multimem)
+        exchange = mdist.PeerExchange((n + m) * d, dev,
+                                      use_multimem={"auto": "auto", "on": True, "off": False}[args.multimem])
         fs = model.flat_state(dev, storage=exchange.storage())
     else:
         fs = model.flat_state(dev)

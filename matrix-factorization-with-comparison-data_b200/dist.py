@@ -136,7 +136,7 @@ class PeerExchange:
     Use:  ex = PeerExchange(numel, dev);  fs = model.flat_state(dev, storage=ex.storage());
           per step: K1 into fs.grads, then ex.step(fs, spec, step)."""
 
-    def __init__(self, numel, device, group=None, use_multimem=True):
+    def __init__(self, numel, device, group=None, use_multimem="auto"):
         import torch.distributed._symmetric_memory as symm_mem
         group = group or dist.group.WORLD
         padded = (numel + 3) // 4 * 4
@@ -152,6 +152,10 @@ class PeerExchange:
         self.peer_grads = (C.c_uint64 * self.world)(*[int(x) for x in self.hg.buffer_ptrs])
         mc_p = int(getattr(self.hp, "multicast_ptr", 0) or 0)
         mc_g = int(getattr(self.hg, "multicast_ptr", 0) or 0)
+        # measured on NVSwitch B200 boxes (profiles/r01_notes.md): in-switch multimem reduction wins at 8 ranks
+        # (0.134 vs 0.163 ms per exchange), plain peer loads win at 2 (0.094 vs 0.139 ms); equal at 4.
+        if use_multimem == "auto":
+            use_multimem = self.world > 4
         self.multimem = bool(use_multimem and mc_p and mc_g)
         self.mc_params, self.mc_grads = (mc_p, mc_g) if self.multimem else (0, 0)
         torch.cuda.synchronize(device)

@@ -33,10 +33,10 @@ for w in 2 4 8; do
   [ $w -gt $N ] && break
   for be in peer nccl; do
     extra=""; [ $be = peer ] && extra="--no-e2e"; [ $be = nccl ] && extra="--no-e2e"
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port 2952$w bench.py --gpus $w --steps 30 --warmup 5 --dp-backend $be $extra > gpurun_out/scale_w${w}_$be.json 2> gpurun_out/scale_w${w}_$be.err
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port 2952$w bench.py --gpus $w --steps 30 --warmup 5 --dp-backend $be --multimem on $extra > gpurun_out/scale_w${w}_$be.json 2> gpurun_out/scale_w${w}_$be.err
     show gpurun_out/scale_w${w}_$be
   done
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port 2953$w bench.py --gpus $w --steps 30 --warmup 5 --dp-backend peer --no-multimem --no-e2e > gpurun_out/scale_w${w}_p2p.json 2> gpurun_out/scale_w${w}_p2p.err
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port 2953$w bench.py --gpus $w --steps 30 --warmup 5 --dp-backend peer --multimem off --no-e2e > gpurun_out/scale_w${w}_p2p.json 2> gpurun_out/scale_w${w}_p2p.err
   show gpurun_out/scale_w${w}_p2p
   # the driver's form of the command (default flags, with e2e)
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port 2954$w bench.py --gpus $w --steps 30 --warmup 5 > gpurun_out/scale_w${w}.json 2> gpurun_out/scale_w${w}.err
