@@ -11,15 +11,16 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
 
-from ._lib import lib, check, ptr, current_stream
+from ._lib import lib, check, ptr, current_stream, MfcdError
 from .store import GroundTruth, compute_device
 
 
-def _row_stats(model, gt: GroundTruth, s: float):
+def _row_stats(model, gt: GroundTruth, s: float, engine=None):
     fs = model.flat_state(gt.device)
     dev = fs.params.device
     n, m, d = fs.n, fs.m, fs.d
@@ -32,8 +33,24 @@ def _row_stats(model, gt: GroundTruth, s: float):
         st = current_stream()
         check(lib.mfcd_table_col_means(ptr(fs.U), n, d, ptr(ubar), st), "mfcd_table_col_means(U)")
         check(lib.mfcd_table_col_means(ptr(fs.V), m, d, ptr(vbar), st), "mfcd_table_col_means(V)")
-        check(lib.mfcd_recon_stats(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar), ptr(vbar),
-                                   ptr(stats), st), "mfcd_recon_stats")
+        engine = os.environ.get("MFCD_K5", "auto") if engine is None else engine
+        done = False
+        if engine in ("auto", "tc"):
+            # tensor-core path (tcgen05 / TMEM) when the shape is eligible; worth it once K = d is big enough
+            # for the fp32 FMA pipe to be the limiter of the SIMT engine
+            if engine == "tc" or d >= 16:
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                rc = lib.mfcd_recon_stats_tc(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar),
+                                             ptr(vbar), ptr(stats), ptr(flag), st)
+                if rc == 0:
+                    if int(flag.item()) != 0:
+                        raise MfcdError("mfcd_recon_stats_tc: tensor-core pipeline timed out")
+                    done = True
+                elif rc != -3 or engine == "tc":          # -3 = MFCD_ERR_UNSUPPORTED -> SIMT engine
+                    check(rc, "mfcd_recon_stats_tc")
+        if not done:
+            check(lib.mfcd_recon_stats(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar), ptr(vbar),
+                                       ptr(stats), st), "mfcd_recon_stats")
     return stats.cpu().numpy(), fs
 
 

@@ -157,3 +157,38 @@ def test_c5_shape_stats_properties(G):
     out = structure.compute_alpha_and_norm_ratios(model, X)
     assert abs(out[0] - 1) < 1e-4 and abs(out[2] - 1) < 1e-4 and out[3] < 1e-3
     assert abs(out[4] - 1) < 1e-5 and abs(out[6] - 1) < 1e-5 and out[8] < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(128, 64, 8), (300, 260, 32), (1000, 1024, 64), (257, 132, 10), (130, 256, 64),
+                                   (64, 4, 3), (513, 1028, 48)])
+def test_tensor_core_recon_stats_matches_simt(G, shape):
+    """tcgen05/TMEM engine (tf32 hi/lo split, 3 MMAs) == fp32 SIMT engine on the six per-row sums."""
+    from mfcd_b200 import metrics
+    from mfcd_b200.store import GroundTruth
+    from mfcd_b200.trainer import MatrixFactorization
+    n, m, d = shape
+    rng = np.random.default_rng(n + m + d)
+    torch.manual_seed(n)
+    model = MatrixFactorization(n, m, d)
+    gt = GroundTruth(X=torch.from_numpy(rng.standard_normal((n, m)).astype(np.float32)))
+    simt, _ = metrics._row_stats(model, gt, 0.7, engine="simt")
+    tcst, _ = metrics._row_stats(model, gt, 0.7, engine="tc")
+    scale = np.abs(simt[:, :6]).max(axis=0) + 1e-30
+    # column 2 is sum(w - rowmean(w)): pure rounding residue around 0, so it is measured against the row's
+    # magnitude sqrt(m * sum (w - a)^2) instead of against itself
+    scale[2] = np.sqrt(m * simt[:, 3]).max() + 1e-30
+    err = np.abs(tcst[:, :6] - simt[:, :6]).max(axis=0) / scale
+    assert (err < 2e-5).all(), err
+    assert np.abs(tcst[:, 6] - simt[:, 6]).max() < 1e-6
+
+
+def test_tensor_core_engine_rejects_ineligible_shapes(G):
+    from mfcd_b200 import metrics
+    from mfcd_b200._lib import MfcdError
+    from mfcd_b200.store import GroundTruth
+    from mfcd_b200.trainer import MatrixFactorization
+    model = MatrixFactorization(40, 30, 128)
+    gt = GroundTruth(X=torch.zeros(40, 30))
+    with pytest.raises(MfcdError):
+        metrics._row_stats(model, gt, 1.0, engine="tc")       # d > 64 and m % 4 != 0
+    metrics._row_stats(model, gt, 1.0, engine="auto")         # falls back to the SIMT engine
