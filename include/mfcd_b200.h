@@ -247,13 +247,15 @@ int mfcd_table_col_means(const float* T, int64_t rows, int32_t d, float* mean, v
 int mfcd_recon_stats(const float* U, const float* V, int64_t n, int64_t m, int32_t d, const mfcd_xview* X,
                      float s, const float* ubar, const float* vbar, double* row_stats, void* stream);
 /* Tensor-core variant of mfcd_recon_stats: 128 x 64 tiles of W from tcgen05.mma (kind::tf32 with a
- * hi/lo operand split, three MMAs per K step, fp32-grade products), accumulators in TMEM, X tiles staged
- * by the bulk async-copy engine.  Eligible when X is dense with 16-byte aligned rows, d <= 64 and
- * m % 4 == 0; otherwise returns MFCD_ERR_UNSUPPORTED (callers then use mfcd_recon_stats).  *error_flag
- * (device int) becomes non-zero if the kernel's internal pipeline timed out. */
+ * hi/lo operand split, three MMAs per K step, fp32-grade products), accumulators in TMEM, operand and X
+ * tiles fed by TMA tensor copies (cp.async.bulk.tensor.2d, 128-byte swizzle).  Eligible when X is dense
+ * with 16-byte aligned rows (ldx % 4 == 0) and d <= 64; otherwise returns MFCD_ERR_UNSUPPORTED and callers
+ * use mfcd_recon_stats.  `workspace` (mfcd_recon_stats_tc_workspace_bytes) holds the split staging tables.
+ * *error_flag (device int) becomes non-zero if the kernel's internal pipeline timed out. */
+int mfcd_recon_stats_tc_workspace_bytes(int64_t n, int64_t m, int32_t d, size_t* bytes);
 int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, int64_t m, int32_t d, const mfcd_xview* X,
                         float s, const float* ubar, const float* vbar, double* row_stats, int32_t* error_flag,
-                        void* stream);
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* rows [r0, r0+nr) of W = U V^T into out (nr x m, row-major): structure.py:389-392
  * sampled rows, and the row blocks the Spearman pass ranks. */
 int mfcd_reconstruct_rows(const float* U, const float* V, int64_t r0, int64_t nr, int64_t m, int32_t d,

@@ -81,7 +81,8 @@ SIGNATURES = {
     "mfcd_philox_uniforms": [U64, U64, I64, P, P],
     "mfcd_table_col_means": [P, I64, I32, P, P],
     "mfcd_recon_stats": [P, P, I64, I64, I32, C.POINTER(XView), F32, P, P, P, P],
-    "mfcd_recon_stats_tc": [P, P, I64, I64, I32, C.POINTER(XView), F32, P, P, P, P, P],
+    "mfcd_recon_stats_tc_workspace_bytes": [I64, I64, I32, C.POINTER(SZ)],
+    "mfcd_recon_stats_tc": [P, P, I64, I64, I32, C.POINTER(XView), F32, P, P, P, P, P, SZ, P],
     "mfcd_reconstruct_rows": [P, P, I64, I64, I64, I32, P, P],
     "mfcd_xview_rows": [C.POINTER(XView), I64, I64, I64, P, P],
     "mfcd_rank_workspace_bytes": [I64, I64, C.POINTER(SZ)],

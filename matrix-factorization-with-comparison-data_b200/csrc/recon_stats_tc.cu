@@ -1,20 +1,24 @@
-// K5 (tensor-core variant): reconstruction statistics with tcgen05 + TMEM + bulk async copies.
+// K5 (tensor-core variant): reconstruction statistics with tcgen05 + TMEM + TMA.
 //
 // Same contract as k_recon_stats (recon_stats.cu; reference structure.py:939-955, :980-1064): one pass over
-// W = U V^T and X that leaves six fp64 sums per row.  Here the 128 x 64 tiles of W are produced by the
-// 5th-generation tensor cores:
-//   * A = 128 rows of U, B = 64 rows of V, both K-major in shared memory with the 128-byte swizzle the
-//     UMMA descriptors expect; operands are split  x = hi + lo  (hi = top 10 mantissa bits, exactly a
-//     TF32 value) and three MMAs  hi.hi + hi.lo + lo.hi  accumulate in TMEM, which restores fp32-grade
-//     products (the reference multiplies in fp32);
-//   * tcgen05.mma (kind::tf32, M=128, N=64, K=8 per instruction) is issued by one elected thread;
-//     accumulators live in TMEM (2 stages x 64 columns) and come back with tcgen05.ld for the epilogue;
-//   * the matching 128 x 64 tile of X -- the only large HBM stream, 4 n m bytes -- is staged by the bulk
-//     async-copy engine (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) two tiles ahead of use;
-//   * warp roles: warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-5 operand producers,
-//     warp 6 TMEM owner + MMA issuer; four mbarriers per stage connect them.
-// Every mbarrier wait is bounded: a pipeline bug sets an error flag and lets the kernel drain instead
-// of hanging the GPU.
+// W = U V^T and X that leaves six fp64 sums per row.  X (4 n m bytes) is the only large stream, so the
+// kernel is organised around keeping that stream moving at HBM speed:
+//   * a tiny pre-pass splits U and V into  hi + lo  (hi = top 10 mantissa bits = an exact TF32 value)
+//     K-padded staging tables, and computes the row / column means of W (a_r = <U_r, vbar>,
+//     b_c = <ubar, V_c>);
+//   * ONE producer thread per CTA feeds everything with TMA tensor copies
+//     (cp.async.bulk.tensor.2d, 128-byte swizzle, zero fill outside the matrices): the A tile (128 rows
+//     of U_hi / U_lo) once per row block, and per 128 x 64 tile the B operand (64 rows of V_hi / V_lo)
+//     and, through a separate ring that runs 2-4 tiles ahead (3-5 slots of 32 KB), the matching X tile;
+//   * ONE thread issues tcgen05.mma (kind::tf32, M = 128, N = 64, K = 8 per instruction), three MMAs per
+//     K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's sgemm), accumulating in TMEM
+//     (2 stages x 64 columns);
+//   * eight epilogue warps (TMEM lane quarter = warp id % 4, column half = warp id / 4) read the
+//     accumulators with tcgen05.ld, the X tile from swizzled shared memory, and fold both into per-row
+//     fp64 sums.
+// mbarriers connect the roles; every wait is bounded, so a pipeline bug raises an error flag and lets
+// the kernel drain instead of hanging the GPU.
+#include <cuda.h>
 #include "internal.h"
 
 namespace mfcd {
@@ -22,29 +26,37 @@ namespace tc {
 
 constexpr int TM = 128;                 // tile rows  (UMMA M, TMEM lanes)
 constexpr int TN = 64;                  // tile cols  (UMMA N, TMEM columns per stage)
-constexpr int KMAX = 64;                // largest (padded) K handled by this kernel
+constexpr int KMAX = 64;                // largest K handled (2 swizzle slabs)
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
-constexpr int A_SLAB_BYTES = TM * 128;  // one K-slab of the A tile
-constexpr int B_SLAB_BYTES = TN * 128;
-constexpr int X_PITCH = TN + 4;         // floats; 272-byte rows keep LDS.128 conflict-free and 16-byte aligned
 constexpr int NSTAGE = 2;
-constexpr int NTHREADS = 7 * 32;
-constexpr int EPI_THREADS = 128;
-constexpr int PROD_THREADS = 64;
+constexpr int EPI_WARPS = 8;            // warp w: TMEM lane quarter w % 4, column half w / 4
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
+constexpr uint32_t A_SLAB_BYTES = TM * 128;
+constexpr uint32_t B_SLAB_BYTES = TN * 128;
+constexpr uint32_t X_BOX_BYTES = TM * 128;   // 128 rows x 32 columns of X
 
-struct Smem {
-  // 1024-byte aligned slabs first
-  float a_hi[2][TM * SLAB_K];
-  float a_lo[2][TM * SLAB_K];
-  float b_hi[NSTAGE][2][TN * SLAB_K];
-  float b_lo[NSTAGE][2][TN * SLAB_K];
-  float xs[NSTAGE][TM * X_PITCH];
-  float b_col[NSTAGE][TN];
-  float vbar[KMAX], ubar[KMAX];
-  unsigned long long bar_full_b[NSTAGE], bar_full_x[NSTAGE], bar_mma_done[NSTAGE], bar_epi_done[NSTAGE];
+constexpr int MAX_RING = 5;              // X-tile ring depth (tiles); 3 fit next to K = 64 operands, 5 next to K <= 32
+constexpr uint32_t XSLOT_BYTES = 2 * X_BOX_BYTES;      // one ring slot = the two 32-column boxes of a tile
+
+// Shared-memory plan (all regions 1024-byte aligned, sizes depend on the number of K slabs):
+//   A  : a_hi[nslab], a_lo[nslab]                 16 KB each
+//   B  : 2 stages x (b_hi[nslab], b_lo[nslab])     8 KB each
+//   X  : ring of `ring` tile slots                 32 KB each
+//   tail: b_col[ring][64], mbarriers, TMEM base, error flag
+struct Tail {
+  float b_col[MAX_RING][TN];
+  unsigned long long x_full[MAX_RING], x_free[MAX_RING];
+  unsigned long long b_full[NSTAGE], mma_done[NSTAGE], tmem_free[NSTAGE], a_full;
   uint32_t tmem_base;
   int error;
 };
+__host__ __device__ constexpr uint32_t a_bytes(int nslab) { return 2u * nslab * A_SLAB_BYTES; }
+__host__ __device__ constexpr uint32_t b_stage_bytes(int nslab) { return 2u * nslab * B_SLAB_BYTES; }
+__host__ __device__ constexpr uint32_t smem_bytes(int nslab, int ring) {
+  return a_bytes(nslab) + NSTAGE * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -68,6 +80,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 }
 // bounded wait: returns false (and raises the CTA's error flag) instead of spinning forever
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* err) {
+  if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*err) return false;
@@ -75,11 +88,17 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t pari
   }
   return true;
 }
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c_inner, int c_outer,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -124,207 +143,270 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// split 4 floats into tf32-exact hi and the remainder lo, store both at the swizzled position of (row, k4)
-__device__ __forceinline__ void store_split(float* hi_slabs, float* lo_slabs, int slab_floats, int row, int k, float4 v) {
-  const int slab = k / SLAB_K;
-  const int chunk = (k % SLAB_K) >> 2;                         // 16-byte chunk inside the 128-byte row
-  const int off = slab * slab_floats + row * SLAB_K + ((chunk ^ (row & 7)) << 2);
-  float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_slabs + off) = h;
-  *reinterpret_cast<float4*>(lo_slabs + off) = l;
+// ---- pre-pass: hi/lo split of a table into K-padded staging arrays + its row-wise dot with `other_mean` ----
+__global__ void __launch_bounds__(256)
+k_split_table(const float* __restrict__ T, int64_t rows, int d, int kpad, const float* __restrict__ other_mean,
+              float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ dots) {
+  const int64_t total = rows * kpad;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / kpad;
+    const int k = (int)(idx - r * kpad);
+    const float v = k < d ? __ldg(T + r * d + k) : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[idx] = h;
+    lo[idx] = v - h;
+  }
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(__ldg(T + r * d + k), __ldg(other_mean + k), acc);
+    dots[r] = acc;
+  }
 }
 
-__device__ __forceinline__ float4 load_row4(const float* __restrict__ T, int64_t row, int64_t rows, int k, int d, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row < rows && k < d) {
-    const float* p = T + row * d + k;
-    if (vec) {
-      v = __ldg(reinterpret_cast<const float4*>(p));
-    } else {
-      v.x = __ldg(p);
-      if (k + 1 < d) v.y = __ldg(p + 1);
-      if (k + 2 < d) v.z = __ldg(p + 2);
-      if (k + 3 < d) v.w = __ldg(p + 3);
-    }
-  }
-  return v;
-}
+struct Maps {
+  CUtensorMap x, u_hi, u_lo, v_hi, v_lo;
+};
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_recon_stats_tc(const float* __restrict__ U, const float* __restrict__ V, int64_t n, int64_t m, int d, int kp,
-                 const float* __restrict__ X, int64_t ldx, float s, const float* __restrict__ ubar_g,
-                 const float* __restrict__ vbar_g, int col_splits, double* __restrict__ row_stats,
-                 int* __restrict__ error_flag) {
+k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp, int ring, float s,
+                 const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
+                 double* __restrict__ row_stats, int* __restrict__ error_flag) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with shared-space arithmetic so the compiler keeps LDS/STS addressing
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  volatile int* err = &sm.error;
-  const bool vec_uv = (d & 3) == 0;
   const int nslab = (kp + SLAB_K - 1) / SLAB_K;
+  unsigned char* a_hi = base;                                     // [nslab] slabs
+  unsigned char* a_lo = a_hi + nslab * A_SLAB_BYTES;
+  unsigned char* b_base = base + a_bytes(nslab);                  // stage st: b_hi[nslab] then b_lo[nslab]
+  unsigned char* x_base = b_base + NSTAGE * b_stage_bytes(nslab); // slot sl: box 0, box 1
+  Tail& tl = *reinterpret_cast<Tail*>(x_base + ring * XSLOT_BYTES);
+  volatile int* err = &tl.error;
   const int64_t row_tiles = (n + TM - 1) / TM;
   const int64_t col_tiles = (m + TN - 1) / TN;
 
   if (threadIdx.x == 0) {
-    sm.error = 0;
-    for (int st = 0; st < NSTAGE; ++st) {
-      mbar_init(&sm.bar_full_b[st], PROD_THREADS);
-      mbar_init(&sm.bar_full_x[st], 1);
-      mbar_init(&sm.bar_mma_done[st], 1);
-      mbar_init(&sm.bar_epi_done[st], EPI_THREADS);
+    tl.error = 0;
+    for (int k = 0; k < MAX_RING; ++k) {
+      mbar_init(&tl.x_full[k], 1);
+      mbar_init(&tl.x_free[k], EPI_THREADS);
     }
+    for (int st = 0; st < NSTAGE; ++st) {
+      mbar_init(&tl.b_full[st], 1);
+      mbar_init(&tl.mma_done[st], 1);
+      mbar_init(&tl.tmem_free[st], EPI_THREADS);
+    }
+    mbar_init(&tl.a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int k = threadIdx.x; k < KMAX; k += NTHREADS) {
-    sm.vbar[k] = k < d ? vbar_g[k] : 0.f;
-    sm.ubar[k] = k < d ? ubar_g[k] : 0.f;
-  }
-  if (warp == 6) tmem_alloc(&sm.tmem_base, NSTAGE * TN);
+  if (warp == MMA_WARP) tmem_alloc(&tl.tmem_base, NSTAGE * TN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t tmem_base = tl.tmem_base;
   const uint32_t idesc = make_idesc(TM, TN);
 
-  uint32_t use = 0;       // tiles processed so far by this CTA: stage = use % 2, phase = (use / 2) & 1
+  uint32_t use = 0;       // tiles processed so far by this CTA: B/TMEM stage = use % 2, X slot = use % ring
+  uint32_t item = 0;      // work items processed so far: phase of a_full
 
-  for (int64_t work = blockIdx.x; work < row_tiles * col_splits; work += gridDim.x) {
+  for (int64_t work = blockIdx.x; work < row_tiles * col_splits; work += gridDim.x, ++item) {
     const int64_t rt = work / col_splits;
     const int split = (int)(work % col_splits);
-    const int64_t row0 = rt * TM;
+    const int row0 = (int)(rt * TM);
     const int64_t ct_begin = col_tiles * split / col_splits;
     const int64_t ct_end = col_tiles * (split + 1) / col_splits;
     const int ntiles = (int)(ct_end - ct_begin);
 
-    // A tile: all threads cooperate; the previous work item's MMAs have completed (its epilogues waited on them)
-    for (int idx = threadIdx.x; idx < TM * (kp >> 2); idx += NTHREADS) {
-      const int row = idx / (kp >> 2), k = (idx % (kp >> 2)) << 2;
-      store_split(&sm.a_hi[0][0], &sm.a_lo[0][0], TM * SLAB_K, row, k, load_row4(U, row0 + row, n, k, d, vec_uv));
-    }
-    fence_proxy_async();
-    __syncthreads();
-
-    if (warp < 4) {
-      // ================= epilogue: thread t owns tile row t (TMEM lane t) =================
-      const int t = threadIdx.x;
-      const int64_t gr = row0 + t;
-      float a_row = 0.f;
-      if (gr < n)
-        for (int k = 0; k < d; ++k) a_row = fmaf(__ldg(U + gr * d + k), sm.vbar[k], a_row);
+    if (warp < EPI_WARPS) {
+      // ===== epilogue: thread owns tile row t (TMEM lane t) and one 32-column half of the tile =====
+      const int t = (warp & 3) * 32 + lane;
+      const int half = warp >> 2;
+      const int64_t gr = (int64_t)row0 + t;
+      const float a_row = gr < n ? __ldg(avec + gr) : 0.f;
+      const int sw = t & 7;
       double acc[6] = {0, 0, 0, 0, 0, 0};
       for (int it = 0; it < ntiles; ++it) {
         const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
+        const uint32_t slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
         const int64_t col0 = (ct_begin + it) * TN;
-        if (!mbar_wait(&sm.bar_mma_done[st], ph, err)) break;
-        if (!mbar_wait(&sm.bar_full_x[st], ph, err)) break;
+        if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
+        if (!mbar_wait(&tl.mma_done[st], ph, err)) break;       // accumulators complete
         tc_fence_after();
-        const float* xrow = &sm.xs[st][t * X_PITCH];
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 16) {
+        const float* xbox = reinterpret_cast<const float*>(x_base + slot * XSLOT_BYTES + half * X_BOX_BYTES) + t * SLAB_K;
+        const float* bcol = &tl.b_col[slot][half * 32];
+        float sx = 0.f, sxx = 0.f, swm = 0.f, sww = 0.f, sxw = 0.f, see = 0.f;
+        const int valid = (int)((m - (col0 + half * 32)) < 32 ? (m - (col0 + half * 32)) : 32);   // columns of this half inside X
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
           float w[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + st * TN + c0, w);
-          float sx = 0.f, sxx = 0.f, sw = 0.f, sww = 0.f, sxw = 0.f, see = 0.f;
+          tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + st * TN + half * 32 + c0, w);
 #pragma unroll
           for (int q = 0; q < 16; q += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(xrow + c0 + q);
+            const int chunk = (c0 + q) >> 2;                       // 16-byte chunk inside the row, un-swizzle
+            const float4 xv = *reinterpret_cast<const float4*>(xbox + ((chunk ^ sw) << 2));
+            const float4 bv = *reinterpret_cast<const float4*>(bcol + c0 + q);
             const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float bs4[4] = {bv.x, bv.y, bv.z, bv.w};
+            if (valid >= 32) {                                     // interior tile: no per-element bounds checks
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (col0 + c0 + q + e < m) {
+              for (int e = 0; e < 4; ++e) {
                 const float x = xs4[e];
                 const float wa = w[q + e] - a_row;
-                const float ee = (w[q + e] - sm.b_col[st][c0 + q + e]) - s * x;
+                const float ee = (w[q + e] - bs4[e]) - s * x;
                 sx += x; sxx = fmaf(x, x, sxx);
-                sw += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
+                swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
                 see = fmaf(ee, ee, see);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (c0 + q + e < valid) {
+                  const float x = xs4[e];
+                  const float wa = w[q + e] - a_row;
+                  const float ee = (w[q + e] - bs4[e]) - s * x;
+                  sx += x; sxx = fmaf(x, x, sxx);
+                  swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
+                  see = fmaf(ee, ee, see);
+                }
               }
             }
           }
-          acc[0] += (double)sx; acc[1] += (double)sxx; acc[2] += (double)sw;
-          acc[3] += (double)sww; acc[4] += (double)sxw; acc[5] += (double)see;
         }
         tc_fence_before();
-        mbar_arrive(&sm.bar_epi_done[st]);
+        mbar_arrive(&tl.x_free[slot]);
+        mbar_arrive(&tl.tmem_free[st]);
+        // 32-element fp32 partials, fp64 across tiles
+        acc[0] += (double)sx; acc[1] += (double)sxx; acc[2] += (double)swm;
+        acc[3] += (double)sww; acc[4] += (double)sxw; acc[5] += (double)see;
       }
       if (gr < n) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) atomicAdd(row_stats + gr * 8 + q, acc[q]);
-        if (split == 0) row_stats[gr * 8 + 6] = (double)a_row;
+        if (split == 0 && half == 0) row_stats[gr * 8 + 6] = (double)a_row;
       }
-    } else if (warp < 6) {
-      // ================= producers: X tile via bulk copies, B tile split + swizzled =================
-      const int pt = threadIdx.x - 128;      // 0..63
-      for (int it = 0; it < ntiles; ++it) {
-        const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
-        const int64_t col0 = (ct_begin + it) * TN;
-        if (u >= NSTAGE) {                    // stage reuse: previous MMAs done with B, previous epilogue done with X
-          if (!mbar_wait(&sm.bar_mma_done[st], ph ^ 1, err)) break;
-          if (!mbar_wait(&sm.bar_epi_done[st], ph ^ 1, err)) break;
-        }
-        const int ncols = (int)((m - col0) < TN ? (m - col0) : TN);
-        const int nrows = (int)((n - row0) < TM ? (n - row0) : TM);
-        if (pt == 0) mbar_arrive_expect_tx(&sm.bar_full_x[st], (uint32_t)(nrows * ncols * 4));
-        __syncwarp();
-        if (warp == 4) {
-          for (int r = lane; r < nrows; r += 32)
-            bulk_g2s(&sm.xs[st][r * X_PITCH], X + (row0 + r) * ldx + col0, (uint32_t)(ncols * 4), &sm.bar_full_x[st]);
-        }
-        // B tile (64 rows of V) and its column means <ubar, V_c>
-        for (int idx = pt; idx < TN * (kp >> 2); idx += PROD_THREADS) {
-          const int row = idx / (kp >> 2), k = (idx % (kp >> 2)) << 2;
-          store_split(&sm.b_hi[st][0][0], &sm.b_lo[st][0][0], TN * SLAB_K, row, k,
-                      load_row4(V, col0 + row, m, k, d, vec_uv));
-        }
-        {
-          const int64_t gc = col0 + pt;
-          float b = 0.f;
-          if (gc < m)
-            for (int k = 0; k < d; ++k) b = fmaf(sm.ubar[k], __ldg(V + gc * d + k), b);
-          sm.b_col[st][pt] = b;
-        }
-        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core's async proxy
-        mbar_arrive(&sm.bar_full_b[st]);
-      }
-    } else {
-      // ================= MMA issuer (one elected thread of warp 6) =================
+    } else if (warp == PRODUCER_WARP) {
+      // ================= TMA producer (one elected thread) =================
       if (lane == 0) {
-        for (int it = 0; it < ntiles; ++it) {
+        bool ok = true;
+        auto issue_x = [&](int it) {
+          const uint32_t u = use + it, slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
+          const int col0 = (int)((ct_begin + it) * TN);
+          if (u >= (uint32_t)ring && !mbar_wait(&tl.x_free[slot], xph ^ 1, err)) { ok = false; return; }
+          mbar_arrive_expect_tx(&tl.x_full[slot], XSLOT_BYTES + TN * (uint32_t)sizeof(float));
+          unsigned char* dst = x_base + slot * XSLOT_BYTES;
+          tma_load_2d(dst, &maps.x, col0, row0, &tl.x_full[slot]);
+          tma_load_2d(dst + X_BOX_BYTES, &maps.x, col0 + SLAB_K, row0, &tl.x_full[slot]);
+          bulk_g2s(&tl.b_col[slot][0], bvec + col0, TN * (uint32_t)sizeof(float), &tl.x_full[slot]);   // bvec padded to 64
+        };
+        // A tile of this row block; the previous block's MMAs are complete (work-item barrier below)
+        mbar_arrive_expect_tx(&tl.a_full, a_bytes(nslab));
+        for (int sl = 0; sl < nslab; ++sl) {
+          tma_load_2d(a_hi + sl * A_SLAB_BYTES, &maps.u_hi, sl * SLAB_K, row0, &tl.a_full);
+          tma_load_2d(a_lo + sl * A_SLAB_BYTES, &maps.u_lo, sl * SLAB_K, row0, &tl.a_full);
+        }
+        for (int it = 0; ok && it < ring - 1 && it < ntiles; ++it) issue_x(it);      // X runs ring-1 tiles ahead
+        for (int it = 0; ok && it < ntiles; ++it) {
           const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
-          if (!mbar_wait(&sm.bar_full_b[st], ph, err)) break;
-          if (u >= NSTAGE && !mbar_wait(&sm.bar_epi_done[st], ph ^ 1, err)) break;   // TMEM stage drained
+          const int col0 = (int)((ct_begin + it) * TN);
+          if (u >= NSTAGE && !mbar_wait(&tl.mma_done[st], ph ^ 1, err)) break;       // B stage free again
+          mbar_arrive_expect_tx(&tl.b_full[st], b_stage_bytes(nslab));
+          unsigned char* bh = b_base + st * b_stage_bytes(nslab);
+          unsigned char* bl = bh + nslab * B_SLAB_BYTES;
+          for (int sl = 0; sl < nslab; ++sl) {
+            tma_load_2d(bh + sl * B_SLAB_BYTES, &maps.v_hi, sl * SLAB_K, col0, &tl.b_full[st]);
+            tma_load_2d(bl + sl * B_SLAB_BYTES, &maps.v_lo, sl * SLAB_K, col0, &tl.b_full[st]);
+          }
+          if (it + ring - 1 < ntiles) issue_x(it + ring - 1);
+        }
+      }
+      __syncwarp();
+    } else {
+      // ================= MMA issuer (one elected thread) =================
+      if (lane == 0) {
+        bool ok = mbar_wait(&tl.a_full, item & 1, err);
+        for (int it = 0; ok && it < ntiles; ++it) {
+          const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
+          if (!mbar_wait(&tl.b_full[st], ph, err)) break;
+          if (u >= NSTAGE && !mbar_wait(&tl.tmem_free[st], ph ^ 1, err)) break;      // TMEM stage drained
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + st * TN;
+          const uint32_t bh = smem_u32(b_base + st * b_stage_bytes(nslab));
+          const uint32_t bl = bh + nslab * B_SLAB_BYTES;
           uint32_t accumulate = 0;
           for (int ks = 0; ks < (kp >> 3); ++ks) {
-            const int slab = ks >> 2, within = (ks & 3) * 32;          // 8 tf32 = 32 bytes per K step
-            const uint64_t a_hi = make_desc(smem_u32(&sm.a_hi[slab][0]) + within);
-            const uint64_t a_lo = make_desc(smem_u32(&sm.a_lo[slab][0]) + within);
-            const uint64_t b_hi = make_desc(smem_u32(&sm.b_hi[st][slab][0]) + within);
-            const uint64_t b_lo = make_desc(smem_u32(&sm.b_lo[st][slab][0]) + within);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, accumulate);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+            const uint32_t slab = ks >> 2, within = (ks & 3) * 32;     // 8 tf32 = 32 bytes per K step
+            const uint64_t d_a_hi = make_desc(smem_u32(a_hi) + slab * A_SLAB_BYTES + within);
+            const uint64_t d_a_lo = make_desc(smem_u32(a_lo) + slab * A_SLAB_BYTES + within);
+            const uint64_t d_b_hi = make_desc(bh + slab * B_SLAB_BYTES + within);
+            const uint64_t d_b_lo = make_desc(bl + slab * B_SLAB_BYTES + within);
+            umma_tf32(d_tmem, d_a_hi, d_b_hi, idesc, accumulate);
+            umma_tf32(d_tmem, d_a_hi, d_b_lo, idesc, 1u);
+            umma_tf32(d_tmem, d_a_lo, d_b_hi, idesc, 1u);
             accumulate = 1u;
           }
-          umma_commit(&sm.bar_mma_done[st]);   // arrives when the MMAs above have finished (implies fence::before_thread_sync)
+          umma_commit(&tl.mma_done[st]);   // arrives when the MMAs above have finished (implies fence::before_thread_sync)
         }
       }
       __syncwarp();
     }
     use += (uint32_t)ntiles;
-    (void)nslab;
     tc_fence_before();
     __syncthreads();                          // work-item boundary: all roles done with this row block
     tc_fence_after();
-    if (sm.error) break;
+    if (tl.error) break;
   }
 
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem_base, NSTAGE * TN);
-  if (threadIdx.x == 0 && sm.error) atomicExch(error_flag, 1);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, NSTAGE * TN);
+  if (threadIdx.x == 0 && tl.error) atomicExch(error_flag, 1);
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 row-major [rows][cols] with leading dimension ld (elements); box = box_rows x 32 columns, 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return MFCD_ERR_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)SLAB_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return MFCD_ERR_ARG; }
+  return MFCD_OK;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+static int kpad_for(int d) { return d <= SLAB_K ? SLAB_K : KMAX; }
+
+struct TcLayout { size_t u_hi, u_lo, v_hi, v_lo, avec, bvec, total; };
+static TcLayout tc_layout(int64_t n, int64_t m, int d) {
+  TcLayout L; size_t off = 0; const int kpad = kpad_for(d);
+  L.u_hi = off; off += align_up(sizeof(float) * n * kpad);
+  L.u_lo = off; off += align_up(sizeof(float) * n * kpad);
+  L.v_hi = off; off += align_up(sizeof(float) * m * kpad);
+  L.v_lo = off; off += align_up(sizeof(float) * m * kpad);
+  L.avec = off; off += align_up(sizeof(float) * n);
+  L.bvec = off; off += align_up(sizeof(float) * ((m + TN - 1) / TN * TN));   // padded: bulk copies read whole tiles
+  L.total = off;
+  return L;
 }
 
 }  // namespace tc
@@ -332,21 +414,59 @@ k_recon_stats_tc(const float* __restrict__ U, const float* __restrict__ V, int64
 
 using namespace mfcd;
 
+static bool tc_eligible(int64_t n, int64_t m, int d, const mfcd_xview* X) {
+  return X && X->X != nullptr && d >= 1 && d <= tc::KMAX && (X->ldx & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(X->X) & 15u) == 0 && n < (int64_t(1) << 31) && m < (int64_t(1) << 31);
+}
+
+extern "C" int mfcd_recon_stats_tc_workspace_bytes(int64_t n, int64_t m, int32_t d, size_t* bytes) {
+  MFCD_REQUIRE(bytes && n >= 1 && m >= 1 && d >= 1, "mfcd_recon_stats_tc_workspace_bytes: bad argument");
+  *bytes = d <= tc::KMAX ? tc::tc_layout(n, m, d).total : 0;
+  return MFCD_OK;
+}
+
 extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, int64_t m, int32_t d,
                                    const mfcd_xview* X, float s, const float* ubar, const float* vbar,
-                                   double* row_stats, int32_t* error_flag, void* stream) {
+                                   double* row_stats, int32_t* error_flag, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   MFCD_REQUIRE(U && V && X && ubar && vbar && row_stats && error_flag, "mfcd_recon_stats_tc: NULL pointer");
   MFCD_REQUIRE(n >= 1 && m >= 1 && d >= 1, "mfcd_recon_stats_tc: bad sizes");
-  // eligibility: dense X with 16-byte aligned rows (bulk copies), K = d padded to a multiple of 8 up to 64
-  if (X->X == nullptr || d > tc::KMAX || (m & 3) != 0 || (X->ldx & 3) != 0 ||
-      (reinterpret_cast<uintptr_t>(X->X) & 15u) != 0) {
-    set_error("mfcd_recon_stats_tc: shape not eligible (needs dense X, d <= 64, m %% 4 == 0, 16-byte aligned rows)");
+  if (!tc_eligible(n, m, d, X)) {
+    set_error("mfcd_recon_stats_tc: shape not eligible (needs dense X with 16-byte aligned rows and d <= 64)");
     return MFCD_ERR_UNSUPPORTED;
   }
+  const tc::TcLayout L = tc::tc_layout(n, m, d);
+  if (workspace == nullptr || workspace_bytes < L.total) {
+    set_error("mfcd_recon_stats_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, L.total);
+    return MFCD_ERR_WORKSPACE;
+  }
   cudaStream_t st = as_stream(stream);
+  char* base = static_cast<char*>(workspace);
+  float* u_hi = reinterpret_cast<float*>(base + L.u_hi);
+  float* u_lo = reinterpret_cast<float*>(base + L.u_lo);
+  float* v_hi = reinterpret_cast<float*>(base + L.v_hi);
+  float* v_lo = reinterpret_cast<float*>(base + L.v_lo);
+  float* avec = reinterpret_cast<float*>(base + L.avec);
+  float* bvec = reinterpret_cast<float*>(base + L.bvec);
+  const int kpad = tc::kpad_for(d);
   const int kp = (d + 7) & ~7;
+
+  tc::Maps maps;
+  int rc;
+  if ((rc = tc::make_map(&maps.x, X->X, n, m, X->ldx, tc::TM)) != MFCD_OK) return rc;
+  if ((rc = tc::make_map(&maps.u_hi, u_hi, n, kpad, kpad, tc::TM)) != MFCD_OK) return rc;
+  if ((rc = tc::make_map(&maps.u_lo, u_lo, n, kpad, kpad, tc::TM)) != MFCD_OK) return rc;
+  if ((rc = tc::make_map(&maps.v_hi, v_hi, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
+  if ((rc = tc::make_map(&maps.v_lo, v_lo, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
+
   MFCD_CUDA(cudaMemsetAsync(row_stats, 0, sizeof(double) * 8 * n, st));
   MFCD_CUDA(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), st));
+  tc::k_split_table<<<grid_for(n * kpad, 256, 8), 256, 0, st>>>(U, n, d, kpad, vbar, u_hi, u_lo, avec);
+  MFCD_CHECK_LAUNCH();
+  MFCD_CUDA(cudaMemsetAsync(bvec, 0, sizeof(float) * ((m + tc::TN - 1) / tc::TN * tc::TN), st));
+  tc::k_split_table<<<grid_for(m * kpad, 256, 8), 256, 0, st>>>(V, m, d, kpad, ubar, v_hi, v_lo, bvec);
+  MFCD_CHECK_LAUNCH();
+
   const int64_t row_tiles = (n + tc::TM - 1) / tc::TM;
   const int64_t col_tiles = (m + tc::TN - 1) / tc::TN;
   const int64_t sms = sm_count();
@@ -355,10 +475,13 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   if (splits > col_tiles) splits = col_tiles;
   int64_t blocks = row_tiles * splits;
   if (blocks > sms) blocks = sms;                                // persistent: one CTA per SM
-  const size_t smem = sizeof(tc::Smem) + 1024;
+  const int nslab = kpad / tc::SLAB_K;
+  int ring = tc::MAX_RING;                                       // deepest X ring that fits in 227 KB
+  while (ring > 2 && tc::smem_bytes(nslab, ring) > 232448u) --ring;
+  const size_t smem = tc::smem_bytes(nslab, ring);
   MFCD_CUDA(cudaFuncSetAttribute(tc::k_recon_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(U, V, n, m, d, kp, X->X, X->ldx, s, ubar, vbar,
-                                                               (int)splits, row_stats, error_flag);
+  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, n, m, kp, ring, s, avec, bvec, (int)splits,
+                                                               row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }

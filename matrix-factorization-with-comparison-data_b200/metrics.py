@@ -40,8 +40,11 @@ def _row_stats(model, gt: GroundTruth, s: float, engine=None):
             # for the fp32 FMA pipe to be the limiter of the SIMT engine
             if engine == "tc" or d >= 16:
                 flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                need = C.c_size_t(0)
+                check(lib.mfcd_recon_stats_tc_workspace_bytes(n, m, d, C.byref(need)), "mfcd_recon_stats_tc_workspace_bytes")
+                ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
                 rc = lib.mfcd_recon_stats_tc(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar),
-                                             ptr(vbar), ptr(stats), ptr(flag), st)
+                                             ptr(vbar), ptr(stats), ptr(flag), ptr(ws), need.value, st)
                 if rc == 0:
                     if int(flag.item()) != 0:
                         raise MfcdError("mfcd_recon_stats_tc: tensor-core pipeline timed out")

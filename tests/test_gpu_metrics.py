@@ -160,7 +160,7 @@ def test_c5_shape_stats_properties(G):
 
 
 @pytest.mark.parametrize("shape", [(128, 64, 8), (300, 260, 32), (1000, 1024, 64), (257, 132, 10), (130, 256, 64),
-                                   (64, 4, 3), (513, 1028, 48)])
+                                   (64, 4, 3), (513, 1028, 48), (5, 8, 2), (2000, 36, 17)])
 def test_tensor_core_recon_stats_matches_simt(G, shape):
     """tcgen05/TMEM engine (tf32 hi/lo split, 3 MMAs) == fp32 SIMT engine on the six per-row sums."""
     from mfcd_b200 import metrics
@@ -190,5 +190,5 @@ def test_tensor_core_engine_rejects_ineligible_shapes(G):
     model = MatrixFactorization(40, 30, 128)
     gt = GroundTruth(X=torch.zeros(40, 30))
     with pytest.raises(MfcdError):
-        metrics._row_stats(model, gt, 1.0, engine="tc")       # d > 64 and m % 4 != 0
+        metrics._row_stats(model, gt, 1.0, engine="tc")       # d > 64 and rows of X not 16-byte aligned
     metrics._row_stats(model, gt, 1.0, engine="auto")         # falls back to the SIMT engine
