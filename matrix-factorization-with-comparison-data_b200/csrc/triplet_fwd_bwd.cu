@@ -74,6 +74,127 @@ __device__ __forceinline__ void smem_add_frag(float* p, const Frag<VEC>& f) {
 template <int NITER, int VAR, bool HOT>
 constexpr int k1_min_blocks() { return NITER > 2 ? 2 : (NITER == 2 ? 3 : (VAR == 0 ? 3 : 4)); }
 
+// One batch of UNR rounds of a warp tile.  Round rr of lane group `grp` handles tile slot grp*LPT + rr, so
+// the slot's "home lane" (the lane that loaded its record) sits in the same group with sub == rr: the score x
+// is parked there with a select and the tile's 32 losses are evaluated once, fully SIMD, after the rounds.
+// CHECK = false for full tiles and rows that exactly fill the lane group (no bounds tests in the hot loop).
+template <int VEC, int LPT, int NITER, int MODE, bool HOT, int UNR, bool CHECK>
+__device__ __forceinline__ void k1_rounds(const float* __restrict__ U, const float* __restrict__ V, const int4& r,
+                                          int slots, int nvalid, int d, float inv_batch, float* __restrict__ gU,
+                                          float* __restrict__ gV, float* __restrict__ gbuf, int64_t base,
+                                          float* my_hot, int lane, float& x_home) {
+  constexpr int GPW = 32 / LPT;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+#pragma unroll 1
+  for (int r0 = 0; r0 < LPT; r0 += UNR) {
+    TripletRows<VEC, LPT, NITER> rows[UNR];
+    int tu[UNR], ti[UNR], tj[UNR], ts[UNR];
+    float tz[UNR];
+    bool ok[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const int e = grp * LPT + r0 + q;                        // tile slot this group handles in this round
+      tu[q] = __shfl_sync(0xffffffffu, r.x, e);
+      ti[q] = __shfl_sync(0xffffffffu, r.y, e);
+      tj[q] = __shfl_sync(0xffffffffu, r.z, e);
+      tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+      ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
+      ok[q] = CHECK ? (e < nvalid) : true;
+      if constexpr (CHECK) {
+        load_rows<VEC, LPT, NITER>(rows[q], U, V, tu[q], ti[q], tj[q], d, sub, ok[q]);
+      } else {
+        const float* pu = U + (int64_t)tu[q] * d;
+        const float* pi = V + (int64_t)ti[q] * d;
+        const float* pj = V + (int64_t)tj[q] * d;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int c = (it * LPT + sub) * VEC;
+          rows[q].uu[it] = ldg_frag<VEC>(pu + c);
+          Frag<VEC> a = ldg_frag<VEC>(pi + c);
+          Frag<VEC> b = ldg_frag<VEC>(pj + c);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) rows[q].dv[it].v[k] = a.v[k] - b.v[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows[q]), 0xffffffffu);
+      x_home = (sub == r0 + q) ? x : x_home;
+      const float p = sigmoidf_ref(x);
+      const float g = bce_grad_score_ref(p, tz[q], inv_batch);
+      if (MODE == 1) {
+        if (ok[q] && sub == 0) gbuf[base + grp * LPT + r0 + q] = g;
+      } else {
+        if (ok[q]) {
+          float* du = gU + (int64_t)tu[q] * d;
+          float* di = gV + (int64_t)ti[q] * d;
+          float* dj = gV + (int64_t)tj[q] * d;
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) {
+            const int c = (it * LPT + sub) * VEC;
+            if (!CHECK || c < d) {
+              Frag<VEC> a, b, nb;
+#pragma unroll
+              for (int kk = 0; kk < VEC; ++kk) {
+                a.v[kk] = g * rows[q].dv[it].v[kk];
+                b.v[kk] = g * rows[q].uu[it].v[kk];
+                nb.v[kk] = -b.v[kk];
+              }
+              red_frag<VEC>(du + c, a);
+              if (!HOT || (ts[q] & 0xff) == 0xff) red_frag<VEC>(di + c, b);
+              if (!HOT || (ts[q] >> 8) == 0xff) red_frag<VEC>(dj + c, nb);
+            }
+          }
+        }
+        if constexpr (HOT) {
+          // updates to privatised rows go to the warp's own shared-memory image.  Lane groups may run
+          // concurrently unless two of them name the same hot row in this round; then they take turns.
+          const bool mine = ok[q] && ts[q] != 0xffff;
+          if (__any_sync(0xffffffffu, mine)) {
+            const int si = ts[q] & 0xff, sj = ts[q] >> 8;
+            bool clash = false;
+#pragma unroll
+            for (int off = LPT; off < 32; off += LPT) {
+              const int o = __shfl_sync(0xffffffffu, ts[q], (lane + off) & 31);
+              const int oi = o & 0xff, oj = o >> 8;
+              clash = clash || (si != 0xff && (si == oi || si == oj)) || (sj != 0xff && (sj == oi || sj == oj));
+            }
+            const bool serial = GPW > 1 && __any_sync(0xffffffffu, clash && mine);
+            auto add_hot = [&]() {
+#pragma unroll
+              for (int it = 0; it < NITER; ++it) {
+                const int c = (it * LPT + sub) * VEC;
+                if (!CHECK || c < d) {
+                  Frag<VEC> b, nb;
+#pragma unroll
+                  for (int kk = 0; kk < VEC; ++kk) {
+                    b.v[kk] = g * rows[q].uu[it].v[kk];
+                    nb.v[kk] = -b.v[kk];
+                  }
+                  if (si != 0xff) smem_add_frag<VEC>(my_hot + si * d + c, b);
+                  if (sj != 0xff) smem_add_frag<VEC>(my_hot + sj * d + c, nb);
+                }
+              }
+            };
+            if (!serial) {
+              if (mine) add_hot();
+              __syncwarp();
+            } else {
+#pragma unroll 1
+              for (int ph = 0; ph < GPW; ++ph) {
+                if (mine && grp == ph) add_hot();
+                __syncwarp();
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int VEC, int LPT, int NITER, int MODE, bool HOT, int VAR = 0>
 __global__ void __launch_bounds__(kBlock, k1_min_blocks<NITER, VAR, HOT>())
 k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
@@ -81,7 +202,6 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
           float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ gbuf,
           float* __restrict__ loss_out /* MODE 0: scalar accumulator; MODE 1: per-block partials */,
           HotRows hot) {
-  constexpr int GPW = 32 / LPT;                                   // triplets side by side in a warp
   constexpr int UNR0 = (NITER > 1 || VAR == 2) ? 2 : 4;
   constexpr int UNR = UNR0 < LPT ? UNR0 : LPT;                    // triplets in flight per group
   __shared__ float s_red[kBlock / 32];
@@ -95,11 +215,9 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
   }
 
   const int lane = threadIdx.x & 31;
-  const int sub = lane % LPT;
-  const int grp = lane / LPT;
-  const unsigned gmask = group_mask<LPT>(lane);
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool exact = (d == LPT * VEC * NITER);                    // every lane of a group owns valid columns
 
   float loss_acc = 0.f;
   for (int64_t base = warp0 * 32; base < B; base += nwarps * 32) {
@@ -113,84 +231,15 @@ k_fwd_bwd(const float* __restrict__ U, const float* __restrict__ V, const mfcd_t
         slots = ((int)__ldg(hot.item_slot + r.y) & 0xff) | (((int)__ldg(hot.item_slot + r.z) & 0xff) << 8);
     }
     const int nvalid = (B - base) < 32 ? (int)(B - base) : 32;
-
-#pragma unroll 1
-    for (int r0 = 0; r0 < LPT; r0 += UNR) {
-      TripletRows<VEC, LPT, NITER> rows[UNR];
-      int tu[UNR], ti[UNR], tj[UNR], ts[UNR];
-      float tz[UNR];
-      bool ok[UNR];
-#pragma unroll
-      for (int q = 0; q < UNR; ++q) {
-        const int e = (r0 + q) * GPW + grp;                      // tile slot this group handles
-        tu[q] = __shfl_sync(0xffffffffu, r.x, e);
-        ti[q] = __shfl_sync(0xffffffffu, r.y, e);
-        tj[q] = __shfl_sync(0xffffffffu, r.z, e);
-        tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
-        ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
-        ok[q] = e < nvalid;
-        load_rows<VEC, LPT, NITER>(rows[q], U, V, tu[q], ti[q], tj[q], d, sub, ok[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < UNR; ++q) {
-        const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows[q]), gmask);
-        const float p = sigmoidf_ref(x);
-        const float g = bce_grad_score_ref(p, tz[q], inv_batch);
-        if (ok[q]) {
-          if (sub == 0) loss_acc += bce_ref(p, tz[q]);
-          if (MODE == 1) {
-            if (sub == 0) gbuf[base + (r0 + q) * GPW + grp] = g;
-          } else if (g != 0.f) {
-            float* du = gU + (int64_t)tu[q] * d;
-            float* di = gV + (int64_t)ti[q] * d;
-            float* dj = gV + (int64_t)tj[q] * d;
-#pragma unroll
-            for (int it = 0; it < NITER; ++it) {
-              const int c = (it * LPT + sub) * VEC;
-              if (c < d) {
-                Frag<VEC> a, b, nb;
-#pragma unroll
-                for (int kk = 0; kk < VEC; ++kk) {
-                  a.v[kk] = g * rows[q].dv[it].v[kk];
-                  b.v[kk] = g * rows[q].uu[it].v[kk];
-                  nb.v[kk] = -b.v[kk];
-                }
-                red_frag<VEC>(du + c, a);
-                if (!HOT || (ts[q] & 0xff) == 0xff) red_frag<VEC>(di + c, b);
-                if (!HOT || (ts[q] >> 8) == 0xff) red_frag<VEC>(dj + c, nb);
-              }
-            }
-          }
-        }
-        if constexpr (HOT && MODE == 0) {
-          // updates to privatised rows: lane groups of the warp take turns on the warp's own image
-          const bool mine = ok[q] && g != 0.f && ts[q] != 0xffff;
-          if (__any_sync(0xffffffffu, mine)) {
-#pragma unroll 1
-            for (int ph = 0; ph < GPW; ++ph) {
-              if (mine && grp == ph) {
-                const int si = ts[q] & 0xff, sj = ts[q] >> 8;
-#pragma unroll
-                for (int it = 0; it < NITER; ++it) {
-                  const int c = (it * LPT + sub) * VEC;
-                  if (c < d) {
-                    Frag<VEC> b, nb;
-#pragma unroll
-                    for (int kk = 0; kk < VEC; ++kk) {
-                      b.v[kk] = g * rows[q].uu[it].v[kk];
-                      nb.v[kk] = -b.v[kk];
-                    }
-                    if (si != 0xff) smem_add_frag<VEC>(my_hot + si * d + c, b);
-                    if (sj != 0xff) smem_add_frag<VEC>(my_hot + sj * d + c, nb);
-                  }
-                }
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-    }
+    float x_home = 0.f;
+    if (exact && nvalid == 32)
+      k1_rounds<VEC, LPT, NITER, MODE, HOT, UNR, false>(U, V, r, slots, nvalid, d, inv_batch, gU, gV, gbuf, base,
+                                                       my_hot, lane, x_home);
+    else
+      k1_rounds<VEC, LPT, NITER, MODE, HOT, UNR, true>(U, V, r, slots, nvalid, d, inv_batch, gU, gV, gbuf, base,
+                                                      my_hot, lane, x_home);
+    // the tile's losses, one triplet per lane
+    if (lane < nvalid) loss_acc += bce_ref(sigmoidf_ref(x_home), __int_as_float(r.w));
   }
 
   if constexpr (HOT && MODE == 0) {

@@ -26,7 +26,7 @@ except Exception as ex:
     print(open(f"gpurun_out/bench_{name}.err").read()[-1500:])
 PY
 }
-S="--steps 10 --warmup 3 --no-cpu-baseline"
+S="--steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
 run_bench c4_hot_B20 --config c4 --batch 1048576 $S
 run_bench c4_hot_B21 --config c4 --batch 2097152 $S
 run_bench c4_hot_B22 --config c4 --batch 4194304 $S
