@@ -65,7 +65,15 @@ struct TripletRows {
   Frag<VEC> dv[NITER];
 };
 
-template <int VEC, int LPT, int NITER>
+// NC = true: read-only (ld.global.nc) path, for kernels that never write the tables;
+// NC = false: coherent loads, for the persistent epoch kernel that updates the tables between steps.
+template <int VEC, bool NC>
+__device__ __forceinline__ Frag<VEC> rd_frag(const float* p) {
+  if constexpr (NC) return ldg_frag<VEC>(p);
+  else return ld_frag<VEC>(p);
+}
+
+template <int VEC, int LPT, int NITER, bool NC = true>
 __device__ __forceinline__ void load_rows(TripletRows<VEC, LPT, NITER>& t, const float* __restrict__ U,
                                           const float* __restrict__ V, int tu, int ti, int tj, int d,
                                           int sub, bool ok) {
@@ -76,9 +84,9 @@ __device__ __forceinline__ void load_rows(TripletRows<VEC, LPT, NITER>& t, const
   for (int it = 0; it < NITER; ++it) {
     const int c = (it * LPT + sub) * VEC;
     if (ok && c < d) {
-      t.uu[it] = ldg_frag<VEC>(pu + c);
-      Frag<VEC> a = ldg_frag<VEC>(pi + c);
-      Frag<VEC> b = ldg_frag<VEC>(pj + c);
+      t.uu[it] = rd_frag<VEC, NC>(pu + c);
+      Frag<VEC> a = rd_frag<VEC, NC>(pi + c);
+      Frag<VEC> b = rd_frag<VEC, NC>(pj + c);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) t.dv[it].v[k] = a.v[k] - b.v[k];
     } else {

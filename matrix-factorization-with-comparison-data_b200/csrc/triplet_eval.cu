@@ -12,47 +12,82 @@ namespace mfcd {
 
 constexpr int kEvalBlock = 256;
 
+// Per-batch loss accumulation that stays accurate for any batch size: a warp keeps a running fp32 sum for the
+// batch it is currently in (tiles are 32 consecutive positions) and issues ONE atomicAdd when the batch index
+// changes -- 64-sample batches cost two atomics, a 4M-sample batch costs one per warp instead of 4M tiny ones.
+struct BatchAcc {
+  int64_t batch;
+  float sum;
+};
+__device__ __forceinline__ void batch_acc_flush(BatchAcc& a, float* __restrict__ batch_out, int64_t N,
+                                                int64_t batch_size, int64_t nb, int lane) {
+  if (a.batch >= 0) {
+    const float t = warp_sum(a.sum);
+    if (lane == 0 && t != 0.f) {
+      const int64_t cnt = (a.batch == nb - 1) ? (N - a.batch * batch_size) : batch_size;
+      atomicAdd(batch_out + a.batch, t / (float)cnt);
+    }
+  }
+  a.batch = -1;
+  a.sum = 0.f;
+}
+// adds this lane's value (for position pos, valid or not) to the warp's running batch sum
+__device__ __forceinline__ void batch_acc_add(BatchAcc& a, float v, int64_t pos, bool valid, float* __restrict__ batch_out,
+                                              int64_t N, int64_t batch_size, int64_t nb, int lane) {
+  const int64_t b = valid ? pos / batch_size : -1;
+  const int64_t b0 = __shfl_sync(0xffffffffu, b, 0);
+  const bool uniform = __all_sync(0xffffffffu, b == b0 || !valid) && b0 >= 0;
+  if (uniform) {                      // the common case: the whole tile lies in one batch
+    if (b0 != a.batch) batch_acc_flush(a, batch_out, N, batch_size, nb, lane), a.batch = b0;
+    a.sum += valid ? v : 0.f;
+  } else {                            // tile straddles batches (or is the ragged end): per-lane atomics
+    batch_acc_flush(a, batch_out, N, batch_size, nb, lane);
+    if (valid) {
+      const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
+      atomicAdd(batch_out + b, v / (float)cnt);
+    }
+  }
+}
+
 template <int VEC, int LPT, int NITER>
 __global__ void __launch_bounds__(kEvalBlock)
 k_eval(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec, int64_t N,
        int d, int64_t batch_size, float* __restrict__ batch_loss, unsigned long long* __restrict__ correct) {
-  constexpr int GPW = 32 / LPT;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const int grp = lane / LPT;
-  const unsigned gmask = group_mask<LPT>(lane);
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t nb = (N + batch_size - 1) / batch_size;
   unsigned int hits = 0;
+  BatchAcc acc{-1, 0.f};
 
   for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
     const int64_t k = base + lane;
     int4 r = make_int4(0, 0, 0, 0);
     if (k < N) r = __ldg(reinterpret_cast<const int4*>(rec) + k);
     const int nvalid = (N - base) < 32 ? (int)(N - base) : 32;
+    float x_home = 0.f;               // score of the slot this lane loaded (see k1_rounds in triplet_fwd_bwd.cu)
 #pragma unroll 2
     for (int rr = 0; rr < LPT; ++rr) {
-      const int e = rr * GPW + grp;
+      const int e = grp * LPT + rr;
       const int tu = __shfl_sync(0xffffffffu, r.x, e);
       const int ti = __shfl_sync(0xffffffffu, r.y, e);
       const int tj = __shfl_sync(0xffffffffu, r.z, e);
-      const float z = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
       const bool ok = e < nvalid;
       TripletRows<VEC, LPT, NITER> rows;
       load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
-      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
-      if (ok && sub == 0) {
-        const float p = sigmoidf_ref(x);
-        const int64_t pos = base + e;
-        const int64_t b = pos / batch_size;
-        const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
-        atomicAdd(batch_loss + b, bce_ref(p, z) / (float)cnt);
-        const float hard = (p > 0.5f) ? 1.f : 0.f;           // (pred > 0.5).float() == z
-        hits += (hard == z) ? 1u : 0u;
-      }
+      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), 0xffffffffu);
+      x_home = (sub == rr) ? x : x_home;
     }
+    const bool valid = lane < nvalid;
+    const float z = __int_as_float(r.w);
+    const float p = sigmoidf_ref(x_home);
+    batch_acc_add(acc, bce_ref(p, z), k, valid, batch_loss, N, batch_size, nb, lane);
+    const float hard = (p > 0.5f) ? 1.f : 0.f;               // (pred > 0.5).float() == z
+    hits += (valid && hard == z) ? 1u : 0u;
   }
+  batch_acc_flush(acc, batch_loss, N, batch_size, nb, lane);
   hits = __reduce_add_sync(0xffffffffu, hits);
   if (lane == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
 }
@@ -76,32 +111,39 @@ static int launch_eval(const float* U, const float* V, const mfcd_triplet* rec, 
 __global__ void __launch_bounds__(256)
 k_gt_eval(mfcd_xview X, const mfcd_triplet* __restrict__ rec, int64_t N, int64_t batch_size,
           float* __restrict__ batch_mse, unsigned long long* __restrict__ correct) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t nb = (N + batch_size - 1) / batch_size;
   unsigned int hits = 0;
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
-    const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + k);
-    const float z = __int_as_float(r.w);
-    const float diff = xview_at(X, r.x, r.y) - xview_at(X, r.x, r.z);   // no scale s (structure.py:1108)
-    const float e = sigmoidf_ref(diff) - z;
-    const int64_t b = k / batch_size;
-    const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
-    atomicAdd(batch_mse + b, e * e / (float)cnt);
-    const float hard = (diff > 0.f) ? 1.f : 0.f;
-    hits += (hard == z) ? 1u : 0u;
+  BatchAcc acc{-1, 0.f};
+  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+    const int64_t k = base + lane;
+    const bool valid = k < N;
+    float e2 = 0.f;
+    if (valid) {
+      const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + k);
+      const float z = __int_as_float(r.w);
+      const float diff = xview_at(X, r.x, r.y) - xview_at(X, r.x, r.z);   // no scale s (structure.py:1108)
+      const float e = sigmoidf_ref(diff) - z;
+      e2 = e * e;
+      const float hard = (diff > 0.f) ? 1.f : 0.f;
+      hits += (hard == z) ? 1u : 0u;
+    }
+    batch_acc_add(acc, e2, k, valid, batch_mse, N, batch_size, nb, lane);
   }
+  batch_acc_flush(acc, batch_mse, N, batch_size, nb, lane);
   hits = __reduce_add_sync(0xffffffffu, hits);
-  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
+  if (lane == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
 }
 
 template <int VEC, int LPT, int NITER>
 __global__ void __launch_bounds__(kEvalBlock)
 k_scores(const float* __restrict__ U, const float* __restrict__ V, const int64_t* __restrict__ u,
          const int64_t* __restrict__ i, const int64_t* __restrict__ j, int64_t N, int d, float* __restrict__ p) {
-  constexpr int GPW = 32 / LPT;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const int grp = lane / LPT;
-  const unsigned gmask = group_mask<LPT>(lane);
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
@@ -109,17 +151,19 @@ k_scores(const float* __restrict__ U, const float* __restrict__ V, const int64_t
     int ru = 0, ri = 0, rj = 0;
     if (k < N) { ru = (int)u[k]; ri = (int)i[k]; rj = (int)j[k]; }
     const int nvalid = (N - base) < 32 ? (int)(N - base) : 32;
+    float x_home = 0.f;
     for (int rr = 0; rr < LPT; ++rr) {
-      const int e = rr * GPW + grp;
+      const int e = grp * LPT + rr;
       const int tu = __shfl_sync(0xffffffffu, ru, e);
       const int ti = __shfl_sync(0xffffffffu, ri, e);
       const int tj = __shfl_sync(0xffffffffu, rj, e);
       const bool ok = e < nvalid;
       TripletRows<VEC, LPT, NITER> rows;
       load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
-      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
-      if (ok && sub == 0) p[base + e] = sigmoidf_ref(x);
+      const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), 0xffffffffu);
+      x_home = (sub == rr) ? x : x_home;
     }
+    if (lane < nvalid) p[k] = sigmoidf_ref(x_home);          // coalesced: one probability per lane
   }
 }
 

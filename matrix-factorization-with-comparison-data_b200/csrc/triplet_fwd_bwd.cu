@@ -322,21 +322,31 @@ int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* re
 //     (row, b) pairs, and a chunked segmented reduction staged through shared
 //     memory with a fix-up pass for rows that straddle chunks.
 constexpr int kSmallB = 256;
+constexpr int kSmallThreads = 1024;     // one CTA; enough lane groups for a group per batch entry
 
-template <int VEC, int LPT, int NITER>
-__global__ void __launch_bounds__(kBlock)
-k_det_small(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
-            const int32_t* __restrict__ perm, int64_t start, int B, int d, float inv_batch,
-            float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ loss_out) {
-  __shared__ int su[kSmallB], si[kSmallB], sj[kSmallB];
-  __shared__ float sg[kSmallB], sl[kSmallB];
-  constexpr int NG = kBlock / LPT;            // groups in the CTA
+struct SmallBatchSmem {
+  int su[kSmallB], si[kSmallB], sj[kSmallB];
+  float sg[kSmallB], sl[kSmallB];
+};
+
+// One deterministic forward + backward of a batch of B <= kSmallB triplets by ONE CTA of kSmallThreads threads.
+// NC selects the read-only load path for the tables.  Must be called by all threads of the CTA.
+// (A persistent one-CTA-per-epoch variant that also ran the optimiser in-kernel was measured and dropped:
+// 20.9 us/step against 14.0 us/step for this kernel + K3 as two launches at config 2, profiles/r01_notes.md.)
+template <int VEC, int LPT, int NITER, bool NC>
+__device__ __forceinline__ void det_small_step(SmallBatchSmem& sm, const float* U, const float* V,
+                                               const mfcd_triplet* __restrict__ rec,
+                                               const int32_t* __restrict__ perm, int64_t start, int B, int d,
+                                               float inv_batch, float* gU, float* gV, float* loss_out) {
+  int* su = sm.su; int* si = sm.si; int* sj = sm.sj;
+  float* sg = sm.sg; float* sl = sm.sl;
+  constexpr int NG = kSmallThreads / LPT;     // groups in the CTA
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const int gid = threadIdx.x / LPT;
   const unsigned gmask = group_mask<LPT>(lane);
 
-  for (int b = threadIdx.x; b < B; b += kBlock) {
+  for (int b = threadIdx.x; b < B; b += kSmallThreads) {
     const int64_t idx = perm ? (int64_t)perm[start + b] : (start + b);
     const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + idx);
     su[b] = r.x; si[b] = r.y; sj[b] = r.z; sg[b] = __int_as_float(r.w);   // sg holds z until phase 1 ends
@@ -351,7 +361,7 @@ k_det_small(const float* __restrict__ U, const float* __restrict__ V, const mfcd
     TripletRows<VEC, LPT, NITER> rows;
     const int tu = ok ? su[b] : 0, ti = ok ? si[b] : 0, tj = ok ? sj[b] : 0;
     const float z = ok ? sg[b] : 0.f;
-    load_rows<VEC, LPT, NITER>(rows, U, V, tu, ti, tj, d, sub, ok);
+    load_rows<VEC, LPT, NITER, NC>(rows, U, V, tu, ti, tj, d, sub, ok);
     const float x = group_sum<LPT>(partial_dot<VEC, LPT, NITER>(rows), gmask);
     const float p = sigmoidf_ref(x);
     __syncwarp(gmask);
@@ -370,76 +380,212 @@ k_det_small(const float* __restrict__ U, const float* __restrict__ V, const mfcd
     if (lane == 0) *loss_out += t * inv_batch;
   }
 
-  // phase 2: gU rows.  Entry b owns row su[b] iff no earlier entry names it.
-  for (int b = gid; b < B; b += NG) {
-    const int row = su[b];
-    bool first = true;
-    for (int t = 0; t < b; ++t) first = first && (su[t] != row);
-    if (!first) continue;
-#pragma unroll
-    for (int it = 0; it < NITER; ++it) {
-      const int c = (it * LPT + sub) * VEC;
-      if (c >= d) continue;
-      Frag<VEC> acc = frag_zero<VEC>();
-      for (int t = b; t < B; ++t) {
-        if (su[t] != row) continue;
-        const float g = sg[t];
-        Frag<VEC> a = ldg_frag<VEC>(V + (int64_t)si[t] * d + c);
-        Frag<VEC> bb = ldg_frag<VEC>(V + (int64_t)sj[t] * d + c);
-#pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) acc.v[kk] += g * (a.v[kk] - bb.v[kk]);
-      }
-      float* dst = gU + (int64_t)row * d + c;
-      Frag<VEC> cur = ld_frag<VEC>(dst);
-#pragma unroll
-      for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc.v[kk];
-      st_frag<VEC>(dst, cur);
-    }
-  }
-
-  // phase 3: gV rows.  A row can be named as i or as j; its owner is the first
-  // entry naming it either way.  sum_i and sum_j are formed separately in
-  // batch order and then added (autograd adds the two index_put_ results).
-  for (int b = gid; b < B; b += NG) {
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-      const int row = side == 0 ? si[b] : sj[b];
-      if (side == 1 && row == si[b]) continue;
+  if constexpr (LPT <= 2) {
+    // narrow rows (d <= 8): a lane group is one or two lanes, so there are up to 256 groups -- every entry
+    // gets its own group and simply walks the batch in shared memory
+    for (int b = gid; b < B; b += NG) {
+      const int row = su[b];
       bool first = true;
-      for (int t = 0; t < b; ++t) first = first && (si[t] != row) && (sj[t] != row);
+      for (int t = 0; t < b; ++t) first = first && (su[t] != row);
       if (!first) continue;
 #pragma unroll
       for (int it = 0; it < NITER; ++it) {
         const int c = (it * LPT + sub) * VEC;
         if (c >= d) continue;
-        Frag<VEC> acc_i = frag_zero<VEC>(), acc_j = frag_zero<VEC>();
+        Frag<VEC> acc = frag_zero<VEC>();
         for (int t = b; t < B; ++t) {
-          const bool hi = si[t] == row, hj = sj[t] == row;
-          if (!hi && !hj) continue;
+          if (su[t] != row) continue;
           const float g = sg[t];
-          Frag<VEC> uu = ldg_frag<VEC>(U + (int64_t)su[t] * d + c);
+          Frag<VEC> a = rd_frag<VEC, NC>(V + (int64_t)si[t] * d + c);
+          Frag<VEC> bb = rd_frag<VEC, NC>(V + (int64_t)sj[t] * d + c);
 #pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) {
-            const float gu = g * uu.v[kk];
-            if (hi) acc_i.v[kk] += gu;
-            if (hj) acc_j.v[kk] -= gu;
-          }
+          for (int kk = 0; kk < VEC; ++kk) acc.v[kk] += g * (a.v[kk] - bb.v[kk]);
         }
-        float* dst = gV + (int64_t)row * d + c;
+        float* dst = gU + (int64_t)row * d + c;
         Frag<VEC> cur = ld_frag<VEC>(dst);
 #pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc_i.v[kk] + acc_j.v[kk];
+        for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc.v[kk];
         st_frag<VEC>(dst, cur);
+      }
+    }
+    for (int b = gid; b < B; b += NG) {
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        const int row = side == 0 ? si[b] : sj[b];
+        if (side == 1 && row == si[b]) continue;
+        bool first = true;
+        for (int t = 0; t < b; ++t) first = first && (si[t] != row) && (sj[t] != row);
+        if (!first) continue;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int c = (it * LPT + sub) * VEC;
+          if (c >= d) continue;
+          Frag<VEC> acc_i = frag_zero<VEC>(), acc_j = frag_zero<VEC>();
+          for (int t = b; t < B; ++t) {
+            const bool hi = si[t] == row, hj = sj[t] == row;
+            if (!hi && !hj) continue;
+            const float g = sg[t];
+            Frag<VEC> uu = rd_frag<VEC, NC>(U + (int64_t)su[t] * d + c);
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) {
+              const float gu = g * uu.v[kk];
+              if (hi) acc_i.v[kk] += gu;
+              if (hj) acc_j.v[kk] -= gu;
+            }
+          }
+          float* dst = gV + (int64_t)row * d + c;
+          Frag<VEC> cur = ld_frag<VEC>(dst);
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc_i.v[kk] + acc_j.v[kk];
+          st_frag<VEC>(dst, cur);
+        }
+      }
+    }
+    return;
+  }
+  // phases 2 and 3: a lane group owns a destination row iff its entry is the first of the batch to name it,
+  // and then sums that row's contributions in batch order.  The scans over the batch are done LPT entries
+  // at a time: every lane of the group tests one entry, a ballot turns the tests into a bit mask, and only
+  // the set bits (the actual matches, ascending) are visited.
+  constexpr unsigned GBITS = (LPT == 32) ? 0xffffffffu : ((1u << LPT) - 1u);
+  const int gshift = (lane / LPT) * LPT;
+  const int entry_rounds = (B + NG - 1) / NG;
+
+  // ---- phase 2: gU rows -------------------------------------------------------------------------------
+  for (int er = 0; er < entry_rounds; ++er) {
+    const int b = er * NG + gid;
+    const bool valid = b < B;
+    const int row = valid ? su[b] : -1;
+    bool owner = valid;
+    Frag<VEC> acc[NITER];
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) acc[it] = frag_zero<VEC>();
+    for (int t0 = 0; t0 < B; t0 += LPT) {
+      const int t = t0 + sub;
+      const bool hit = valid && t < B && su[t] == row;
+      unsigned m = (__ballot_sync(0xffffffffu, hit) >> gshift) & GBITS;
+      if (!valid) continue;
+      // bits for entries before b: somebody earlier names the row -> not the owner
+      const int rel = b - t0;                                  // entry b sits at bit `rel` of this chunk (if 0 <= rel < LPT)
+      const unsigned before = rel <= 0 ? 0u : (rel >= LPT ? GBITS : ((1u << rel) - 1u));
+      if (m & before) owner = false;
+      m &= ~before;
+      if (!owner) continue;
+      while (m) {                                              // matches at or after b, ascending = batch order
+        const int tt = t0 + __ffs(m) - 1;
+        m &= m - 1;
+        const float g = sg[tt];
+        const float* pi = V + (int64_t)si[tt] * d;
+        const float* pj = V + (int64_t)sj[tt] * d;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int c = (it * LPT + sub) * VEC;
+          if (c < d) {
+            Frag<VEC> a = rd_frag<VEC, NC>(pi + c);
+            Frag<VEC> bb = rd_frag<VEC, NC>(pj + c);
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) acc[it].v[kk] += g * (a.v[kk] - bb.v[kk]);
+          }
+        }
+      }
+    }
+    if (owner) {
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) {
+        const int c = (it * LPT + sub) * VEC;
+        if (c < d) {
+          float* dst = gU + (int64_t)row * d + c;
+          Frag<VEC> cur = ld_frag<VEC>(dst);
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc[it].v[kk];
+          st_frag<VEC>(dst, cur);
+        }
+      }
+    }
+  }
+
+  // ---- phase 3: gV rows.  A row can be named as i or as j; its owner is the first entry naming it either
+  // way.  sum_i and sum_j are formed separately in batch order and then added (autograd adds the two
+  // index_put_ results).
+  const int task_rounds = (2 * B + NG - 1) / NG;          // task = (entry, side): both sides run side by side
+  for (int er = 0; er < task_rounds; ++er) {
+    const int task = er * NG + gid;
+    const int b = task >> 1;
+    {
+      const int side = task & 1;
+      const bool valid = b < B && !(side == 1 && sj[b] == si[b]);
+      const int row = valid ? (side == 0 ? si[b] : sj[b]) : -1;
+      bool owner = valid;
+      Frag<VEC> acc_i[NITER], acc_j[NITER];
+#pragma unroll
+      for (int it = 0; it < NITER; ++it) { acc_i[it] = frag_zero<VEC>(); acc_j[it] = frag_zero<VEC>(); }
+      for (int t0 = 0; t0 < B; t0 += LPT) {
+        const int t = t0 + sub;
+        const bool in = valid && t < B;
+        unsigned mi = (__ballot_sync(0xffffffffu, in && si[t] == row) >> gshift) & GBITS;
+        unsigned mj = (__ballot_sync(0xffffffffu, in && sj[t] == row) >> gshift) & GBITS;
+        if (!valid) continue;
+        const int rel = b - t0;
+        const unsigned before = rel <= 0 ? 0u : (rel >= LPT ? GBITS : ((1u << rel) - 1u));
+        if ((mi | mj) & before) owner = false;
+        // side 1 (row = sj[b]): entry b itself names the row only as j; as i it names a different row
+        mi &= ~before;
+        mj &= ~before;
+        if (!owner) continue;
+        unsigned m = mi | mj;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int tt = t0 + bit;
+          const float g = sg[tt];
+          const float* pu = U + (int64_t)su[tt] * d;
+          const bool hi = (mi >> bit) & 1u, hj = (mj >> bit) & 1u;
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) {
+            const int c = (it * LPT + sub) * VEC;
+            if (c < d) {
+              Frag<VEC> uu = rd_frag<VEC, NC>(pu + c);
+#pragma unroll
+              for (int kk = 0; kk < VEC; ++kk) {
+                const float gu = g * uu.v[kk];
+                if (hi) acc_i[it].v[kk] += gu;
+                if (hj) acc_j[it].v[kk] -= gu;
+              }
+            }
+          }
+        }
+      }
+      if (owner) {
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int c = (it * LPT + sub) * VEC;
+          if (c < d) {
+            float* dst = gV + (int64_t)row * d + c;
+            Frag<VEC> cur = ld_frag<VEC>(dst);
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc_i[it].v[kk] + acc_j[it].v[kk];
+            st_frag<VEC>(dst, cur);
+          }
+        }
       }
     }
   }
 }
 
 template <int VEC, int LPT, int NITER>
+__global__ void __launch_bounds__(kSmallThreads)
+k_det_small(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
+            const int32_t* __restrict__ perm, int64_t start, int B, int d, float inv_batch,
+            float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ loss_out) {
+  __shared__ SmallBatchSmem sm;
+  det_small_step<VEC, LPT, NITER, true>(sm, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss_out);
+}
+
+template <int VEC, int LPT, int NITER>
 struct DetSmallLauncher {
   static int run(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
                  int B, int d, float inv_batch, float* gU, float* gV, float* loss, cudaStream_t st) {
-    k_det_small<VEC, LPT, NITER><<<1, kBlock, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss);
+    k_det_small<VEC, LPT, NITER><<<1, kSmallThreads, 0, st>>>(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss);
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
