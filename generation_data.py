@@ -8,9 +8,10 @@ work runs in the CUDA samplers of mfcd_b200 (kernels K7).  With
 replay the reference's host generators instead, so a seeded run reproduces the
 reference's triplets bit for bit (parity runs at reference scale).
 
-The reference's other five strategies and ten generators are outside the
-accelerated path; asking for them raises
-NotImplementedError rather than silently running something else.
+proximity / variance / top_k (the strategies Runs.ipynb cell 18 sweeps) run on the same
+GPU machinery (per-user top-k lists or an item law + the shared dedup).  The reference's "not used" strategies
+(cluster, user_similarity) and its ten other generators are outside the accelerated path; asking for them
+raises NotImplementedError rather than silently running something else.
 """
 import os
 
@@ -94,9 +95,24 @@ def _outside_hot_path(name):
     return fn
 
 
-choose_items_by_proximity = _outside_hot_path("choose_items_by_proximity")
-choose_items_by_variance = _outside_hot_path("choose_items_by_variance")
-choose_items_top_k = _outside_hot_path("choose_items_top_k")
+# === PROXIMITY a.k.a. MIN-MAX ===  (generation_data.py:29-43)
+def choose_items_by_proximity(X, num_triplets, exclude, k=100):
+    """i among the user's k highest scores, j among the k lowest."""
+    return _sampling.sample_proximity(X, num_triplets, _as_exclude(exclude), k=k)
+
+
+# === VARIANCE ===  (generation_data.py:87-99)
+def choose_items_by_variance(X, num_triplets, exclude):
+    """item pair drawn without replacement with probability proportional to the item's variance across users."""
+    return _sampling.sample_variance(X, num_triplets, _as_exclude(exclude))
+
+
+# === TOP-K a.k.a. TOP_10% ===  (generation_data.py:189-224)
+def choose_items_top_k(X, num_triplets, exclude, k=None):
+    """i != j among the user's top-k items (k = 10% of the items, at least 5); at most 3 x num_triplets attempts."""
+    return _sampling.sample_top_k(X, num_triplets, _as_exclude(exclude), k=k)
+
+
 choose_items_cluster_based = _outside_hot_path("choose_items_cluster_based")
 choose_items_by_user_similarity = _outside_hot_path("choose_items_by_user_similarity")
 

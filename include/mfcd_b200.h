@@ -210,6 +210,13 @@ int mfcd_sample_block(int64_t m, int64_t count, uint64_t seed, uint64_t counter0
                       const int32_t* top_users, int64_t n_top_users, const int32_t* top_items,
                       int64_t n_top_items, uint64_t* keys, void* stream);
 
+/* Per-user candidate lists (next-ring strategies of SURVEY 8f): list_i is n x ki, list_j is n x kj item ids;
+ * u ~ U[0,n), i ~ U(list_i[u]), j ~ U(list_j[u]).  proximity (generation_data.py:29-43): top-k and bottom-k
+ * lists; top_k (generation_data.py:189-224): same_list = 1, one list, j drawn among the other k-1 entries. */
+int mfcd_sample_lists(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                      const int32_t* list_i, int32_t ki, const int32_t* list_j, int32_t kj, int32_t same_list,
+                      uint64_t* keys, void* stream);
+
 /* Sequential "accept if new" over a candidate stream, done with a stable sort:
  * candidate c is accepted iff keys[c] != NONE, it equals no seen[] key and no
  * earlier candidate; the first `want` accepted keys are written, in stream

@@ -75,6 +75,7 @@ SIGNATURES = {
     "mfcd_sample_margin": [I64, I64, I64, U64, U64, C.POINTER(XView), F32, P, P],
     "mfcd_sample_popularity": [I64, I64, I64, U64, U64, P, P, P],
     "mfcd_sample_block": [I64, I64, U64, U64, P, I64, P, I64, P, P],
+    "mfcd_sample_lists": [I64, I64, I64, U64, U64, P, I32, P, I32, I32, P, P],
     "mfcd_unique_workspace_bytes": [I64, I64, C.POINTER(SZ)],
     "mfcd_unique_accept": [P, I64, P, I64, I64, P, P, P, SZ, P],
     "mfcd_btl_labels": [C.POINTER(XView), P, I64, I64, I32, F32, I32, U64, P, P, P],

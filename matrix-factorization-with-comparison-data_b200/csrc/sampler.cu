@@ -90,6 +90,31 @@ k_sample_block(int64_t m, int64_t count, uint64_t seed, uint64_t counter0, const
   }
 }
 
+// proximity (generation_data.py:29-43) and top_k (generation_data.py:189-224): per-user candidate lists
+// (the user's top / bottom items by X[u], built once by the caller); i ~ U(list_i[u]), j ~ U(list_j[u]).
+// same_list != 0: both items come from one list and must differ (top_k redraws j until it does: drawing
+// j uniformly among the other k-1 positions is the same law).
+__global__ void __launch_bounds__(256)
+k_sample_lists(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+               const int32_t* __restrict__ list_i, int ki, const int32_t* __restrict__ list_j, int kj, int same_list,
+               uint64_t* __restrict__ keys) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < count; c += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = Philox::run(seed, counter0 + (uint64_t)c, 0u);
+    const uint32_t u = bounded(r.x, (uint32_t)n);
+    const uint32_t a = bounded(r.y, (uint32_t)ki);
+    uint32_t b;
+    if (same_list) {
+      b = bounded(r.z, (uint32_t)(kj - 1));
+      if (b >= a) ++b;
+    } else {
+      b = bounded(r.z, (uint32_t)kj);
+    }
+    const uint32_t i = (uint32_t)__ldg(list_i + (int64_t)u * ki + a);
+    const uint32_t j = (uint32_t)__ldg(list_j + (int64_t)u * kj + b);
+    keys[c] = (i != j) ? make_key(u, i, j, m) : MFCD_KEY_NONE;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // sequential-accept semantics through a stable sort
 // ---------------------------------------------------------------------------
@@ -250,6 +275,19 @@ extern "C" int mfcd_sample_block(int64_t m, int64_t count, uint64_t seed, uint64
   MFCD_REQUIRE(top_users && top_items && keys, "mfcd_sample_block: NULL pointer");
   k_sample_block<<<grid_for(count, 256, 8), 256, 0, as_stream(stream)>>>(m, count, seed, counter0, top_users,
                                                                          n_top_users, top_items, n_top_items, keys);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_sample_lists(int64_t n, int64_t m, int64_t count, uint64_t seed, uint64_t counter0,
+                                 const int32_t* list_i, int32_t ki, const int32_t* list_j, int32_t kj,
+                                 int32_t same_list, uint64_t* keys, void* stream) {
+  int rc = check_nm("mfcd_sample_lists", n, m, count, keys);
+  if (rc != MFCD_OK || count == 0) return rc;
+  MFCD_REQUIRE(list_i && list_j && ki >= 1 && kj >= 1, "mfcd_sample_lists: bad lists");
+  MFCD_REQUIRE(!same_list || (ki == kj && ki >= 2), "mfcd_sample_lists: same_list needs one list of >= 2 items");
+  k_sample_lists<<<grid_for(count, 256, 8), 256, 0, as_stream(stream)>>>(n, m, count, seed, counter0, list_i, ki,
+                                                                         list_j, kj, same_list, keys);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }

@@ -236,6 +236,68 @@ def sample_svd(X, num_triplets, exclude=None, rank=10, top_fraction=0.3, seed=No
     return TripletSet(keys, n, m)
 
 
+def _topk_lists(gt: GroundTruth, k, largest=True, chunk_rows=4096):
+    """(n x k) int32 table of each user's k largest (or smallest) items by X[u] (torch.topk: library call)."""
+    n, m = gt.shape
+    out = torch.empty((n, k), dtype=torch.int32, device=gt.device)
+    for r0 in range(0, n, chunk_rows):
+        rows = gt.rows(r0, min(chunk_rows, n - r0))
+        out[r0:r0 + rows.shape[0]] = torch.topk(rows, k, dim=1, largest=largest).indices.to(torch.int32)
+    return out.contiguous()
+
+
+def _sample_lists(gt, num_triplets, exclude, list_i, list_j, same_list, seed, max_attempts=None):
+    n, m = gt.shape
+    dev = gt.device
+    seed = fresh_seed() if seed is None else seed
+    with torch.cuda.device(dev):
+        def draw(count, c0, out):
+            check(lib.mfcd_sample_lists(n, m, count, seed, c0, ptr(list_i), list_i.shape[1], ptr(list_j),
+                                        list_j.shape[1], int(same_list), ptr(out), current_stream()), "mfcd_sample_lists")
+        keys, attempts = _accept_rounds(draw, n, m, num_triplets, keys_from_triplets(exclude, m, dev), dev,
+                                        max_attempts=max_attempts)
+    return TripletSet(keys, n, m), attempts
+
+
+def sample_proximity(X, num_triplets, exclude=None, k=100, seed=None):
+    """i among the user's top-k items, j among the bottom-k (generation_data.py:29-43)."""
+    gt = GroundTruth.wrap(X)
+    kk = min(k, gt.shape[1])
+    ts, _ = _sample_lists(gt, num_triplets, exclude, _topk_lists(gt, kk, True), _topk_lists(gt, kk, False), False, seed)
+    return ts
+
+
+def sample_top_k(X, num_triplets, exclude=None, k=None, seed=None):
+    """i != j among the user's top-k items, k = min(m, max(5, int(0.1 m))), at most 3 x num_triplets attempts
+    (generation_data.py:189-224)."""
+    gt = GroundTruth.wrap(X)
+    m = gt.shape[1]
+    if k is None:
+        k = min(m, max(5, int(0.1 * m)))
+    top = _topk_lists(gt, k, True)
+    ts, _ = _sample_lists(gt, num_triplets, exclude, top, top, True, seed, max_attempts=num_triplets * 3)
+    if len(ts) < num_triplets:
+        print(f"⚠️ Only {len(ts)} triplets generated (target={num_triplets}, k={k})")
+    return ts
+
+
+def sample_variance(X, num_triplets, exclude=None, seed=None):
+    """item pair without replacement from probabilities proportional to the item's variance across users
+    (generation_data.py:87-99): the popularity sampler with a different law."""
+    gt = GroundTruth.wrap(X)
+    n, m = gt.shape
+    dev = gt.device
+    var = torch.var(gt.dense(), dim=0).double()
+    cdf = torch.cumsum(var / var.sum(), dim=0).contiguous()
+    seed = fresh_seed() if seed is None else seed
+    with torch.cuda.device(dev):
+        def draw(count, c0, out):
+            check(lib.mfcd_sample_popularity(n, m, count, seed, c0, ptr(cdf), ptr(out), current_stream()),
+                  "mfcd_sample_popularity")
+        keys, _ = _accept_rounds(draw, n, m, num_triplets, keys_from_triplets(exclude, m, dev), dev, first_rate=0.5)
+    return TripletSet(keys, n, m)
+
+
 # ---------------------------------------------------------------------------
 # K8: labels
 # ---------------------------------------------------------------------------

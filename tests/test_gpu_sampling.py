@@ -218,3 +218,32 @@ def test_split_device_mode_contract(G):
     assert len(np.intersect1d(allk[0], allk[1])) == 0 and len(np.intersect1d(allk[0], allk[2])) == 0
     batch = next(iter(va))
     assert batch[0].dtype == torch.int64 and batch[3].dtype == torch.float64 and len(batch[0]) == 30
+
+
+@pytest.mark.parametrize("strategy", ["proximity", "top_k", "variance"])
+def test_next_ring_strategies(G, strategy):
+    """the strategies Runs.ipynb cell 18 sweeps besides the four hot-path ones"""
+    import structure
+    rng = np.random.default_rng(8)
+    n, m = 60, 80
+    Xn = rng.standard_normal((n, m)).astype(np.float32)
+    X = torch.from_numpy(Xn)
+    torch.manual_seed(2)
+    num = 500
+    ts = structure.get_triplets_from_X(X, num, strategy=strategy)
+    t = np.array(ts.tolist(), np.int64)
+    assert len(t) == num == len({tuple(r) for r in t.tolist()}) and (t[:, 1] != t[:, 2]).all()
+    order = np.argsort(-Xn, axis=1)
+    rank = np.empty_like(order); np.put_along_axis(rank, order, np.arange(m)[None, :].repeat(n, 0), 1)
+    if strategy == "proximity":      # i in the user's top-k, j in the bottom-k (k = min(100, m) = m here -> any)
+        ts2 = structure.choose_items_by_proximity(X, 300, None, k=10)
+        t2 = np.array(ts2.tolist(), np.int64)
+        assert (rank[t2[:, 0], t2[:, 1]] < 10).all() and (rank[t2[:, 0], t2[:, 2]] >= m - 10).all()
+    if strategy == "top_k":          # k = max(5, int(0.1 m)) = 8
+        assert (rank[t[:, 0], t[:, 1]] < 8).all() and (rank[t[:, 0], t[:, 2]] < 8).all()
+    if strategy == "variance":       # high-variance items are drawn more often
+        Xv = Xn.copy(); Xv[:, :5] *= 6.0
+        tv = np.array(structure.get_triplets_from_X(torch.from_numpy(Xv), 2000, strategy="variance").tolist(), np.int64)
+        assert (tv[:, 1:] < 5).mean() > 0.5
+    more = structure.get_triplets_from_X(X, 40, strategy=strategy, exclude=ts)
+    assert not ({tuple(r) for r in more.tolist()} & {tuple(r) for r in t.tolist()})

@@ -70,7 +70,7 @@ def test_unknown_names_raise_like_the_reference():
     with pytest.raises(NotImplementedError):
         structure.generate_X(5, 5, 2, "cpu", generation="gmm")
     with pytest.raises(NotImplementedError):
-        structure.get_triplets_from_X(X, 3, strategy="top_k")
+        structure.get_triplets_from_X(X, 3, strategy="cluster")
 
 
 def test_reference_rng_replay_random_sampler():
