@@ -45,13 +45,18 @@ static inline bool row_shape_for(int d, RowShape* s) {
       }                                                                     \
   }
 
-#define MFCD_DISPATCH_ROW_SHAPE(L, d, ...)                                  \
+// MINLPT widens the lane group beyond what the row needs (extra lanes hold zeros): the small-batch
+// deterministic kernel uses its groups for batch scans too and wants at least 8 lanes per group.
+#define MFCD_DISPATCH_ROW_SHAPE(L, d, ...) MFCD_DISPATCH_ROW_SHAPE_MIN(L, d, 1, __VA_ARGS__)
+
+#define MFCD_DISPATCH_ROW_SHAPE_MIN(L, d, MINLPT, ...)                      \
   do {                                                                      \
     ::mfcd::RowShape shape;                                                 \
     if (!::mfcd::row_shape_for((d), &shape)) {                              \
       ::mfcd::set_error("unsupported embedding width d=%d (need d <= 512 for d%%4==0, <= 256 for even d, <= 128 otherwise)", (int)(d)); \
       return MFCD_ERR_UNSUPPORTED;                                          \
     }                                                                       \
+    if (shape.lpt < (MINLPT)) shape.lpt = (MINLPT);                         \
     if (shape.vec == 4) { MFCD_DISPATCH_LPT(L, 4, __VA_ARGS__) }            \
     else if (shape.vec == 2) { MFCD_DISPATCH_LPT(L, 2, __VA_ARGS__) }       \
     else { MFCD_DISPATCH_LPT(L, 1, __VA_ARGS__) }                           \

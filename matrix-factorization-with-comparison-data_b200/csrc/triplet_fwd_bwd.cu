@@ -380,69 +380,6 @@ __device__ __forceinline__ void det_small_step(SmallBatchSmem& sm, const float* 
     if (lane == 0) *loss_out += t * inv_batch;
   }
 
-  if constexpr (LPT <= 2) {
-    // narrow rows (d <= 8): a lane group is one or two lanes, so there are up to 256 groups -- every entry
-    // gets its own group and simply walks the batch in shared memory
-    for (int b = gid; b < B; b += NG) {
-      const int row = su[b];
-      bool first = true;
-      for (int t = 0; t < b; ++t) first = first && (su[t] != row);
-      if (!first) continue;
-#pragma unroll
-      for (int it = 0; it < NITER; ++it) {
-        const int c = (it * LPT + sub) * VEC;
-        if (c >= d) continue;
-        Frag<VEC> acc = frag_zero<VEC>();
-        for (int t = b; t < B; ++t) {
-          if (su[t] != row) continue;
-          const float g = sg[t];
-          Frag<VEC> a = rd_frag<VEC, NC>(V + (int64_t)si[t] * d + c);
-          Frag<VEC> bb = rd_frag<VEC, NC>(V + (int64_t)sj[t] * d + c);
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) acc.v[kk] += g * (a.v[kk] - bb.v[kk]);
-        }
-        float* dst = gU + (int64_t)row * d + c;
-        Frag<VEC> cur = ld_frag<VEC>(dst);
-#pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc.v[kk];
-        st_frag<VEC>(dst, cur);
-      }
-    }
-    for (int b = gid; b < B; b += NG) {
-#pragma unroll 1
-      for (int side = 0; side < 2; ++side) {
-        const int row = side == 0 ? si[b] : sj[b];
-        if (side == 1 && row == si[b]) continue;
-        bool first = true;
-        for (int t = 0; t < b; ++t) first = first && (si[t] != row) && (sj[t] != row);
-        if (!first) continue;
-#pragma unroll
-        for (int it = 0; it < NITER; ++it) {
-          const int c = (it * LPT + sub) * VEC;
-          if (c >= d) continue;
-          Frag<VEC> acc_i = frag_zero<VEC>(), acc_j = frag_zero<VEC>();
-          for (int t = b; t < B; ++t) {
-            const bool hi = si[t] == row, hj = sj[t] == row;
-            if (!hi && !hj) continue;
-            const float g = sg[t];
-            Frag<VEC> uu = rd_frag<VEC, NC>(U + (int64_t)su[t] * d + c);
-#pragma unroll
-            for (int kk = 0; kk < VEC; ++kk) {
-              const float gu = g * uu.v[kk];
-              if (hi) acc_i.v[kk] += gu;
-              if (hj) acc_j.v[kk] -= gu;
-            }
-          }
-          float* dst = gV + (int64_t)row * d + c;
-          Frag<VEC> cur = ld_frag<VEC>(dst);
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) cur.v[kk] += acc_i.v[kk] + acc_j.v[kk];
-          st_frag<VEC>(dst, cur);
-        }
-      }
-    }
-    return;
-  }
   // phases 2 and 3: a lane group owns a destination row iff its entry is the first of the batch to name it,
   // and then sums that row's contributions in batch order.  The scans over the batch are done LPT entries
   // at a time: every lane of the group tests one entry, a ballot turns the tests into a bit mask, and only
@@ -594,7 +531,8 @@ struct DetSmallLauncher {
 static int launch_det_small(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                             int64_t start, int B, int d, float inv_batch, float* gU, float* gV, float* loss,
                             cudaStream_t st) {
-  MFCD_DISPATCH_ROW_SHAPE(DetSmallLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, st);
+  // at least 8 lanes per group: the groups also scan the batch, 8 entries per ballot (narrow rows idle the rest)
+  MFCD_DISPATCH_ROW_SHAPE_MIN(DetSmallLauncher, d, 8, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, st);
 }
 
 }  // namespace mfcd
