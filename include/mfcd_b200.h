@@ -69,6 +69,11 @@ int mfcd_pack_triplets(const int64_t* u, const int64_t* i, const int64_t* j, con
                        int64_t N, mfcd_triplet* out, void* stream);
 int mfcd_unpack_triplets(const mfcd_triplet* rec, int64_t N, int64_t* u, int64_t* i, int64_t* j,
                          double* z, void* stream);
+/* 8-byte wire format for HARD-labelled records, for host <-> device staging (PCIe moves half the bytes):
+ * bit 0 = label, bits [1,21) = j, [21,41) = i, [41,64) = u  (n_users <= 2^23, n_items <= 2^20).
+ * pack sets *bad (device int, caller zeroes it) if a record has a soft label or an index out of range. */
+int mfcd_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t* bad, void* stream);
+int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_triplet* out, void* stream);
 /* out[k] = rec[perm[k]] for k in [0,N): materialise one epoch's shuffled order
  * (replaces RandomSampler + default_collate, structure.py:738, :845). */
 int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N, mfcd_triplet* out,

@@ -56,6 +56,8 @@ SIGNATURES = {
     "mfcd_device_sm_count": [C.POINTER(C.c_int)],
     "mfcd_pack_triplets": [P, P, P, P, I64, P, P],
     "mfcd_unpack_triplets": [P, I64, P, P, P, P, P],
+    "mfcd_pack_triplets8": [P, I64, P, P, P],
+    "mfcd_unpack_triplets8": [P, I64, P, P],
     "mfcd_gather_triplets": [P, P, I64, P, P],
     "mfcd_triplet_fwd_bwd": [P, P, P, P, I64, I64, I32, F32, P, P, P, P],
     "mfcd_max_hot_items": [I32, C.POINTER(I32)],

@@ -57,9 +57,53 @@ __global__ void k_gather(const mfcd_triplet* __restrict__ rec, const int32_t* __
   }
 }
 
+// 8-byte wire format for hard-labelled comparisons (host <-> device transfers are PCIe-bound at 16 B/triplet):
+// bits [0,1) label, [1,21) j, [21,41) i, [41,64) u  =>  n_users <= 2^23, n_items <= 2^20.
+__global__ void k_pack8(const mfcd_triplet* __restrict__ rec, int64_t N, unsigned long long* __restrict__ out,
+                        int* __restrict__ bad) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    const int4 r = __ldg(reinterpret_cast<const int4*>(rec) + k);
+    const float z = __int_as_float(r.w);
+    if ((z != 0.f && z != 1.f) || (unsigned)r.x >= (1u << 23) || (unsigned)r.y >= (1u << 20) || (unsigned)r.z >= (1u << 20))
+      atomicExch(bad, 1);
+    out[k] = ((unsigned long long)(unsigned)r.x << 41) | ((unsigned long long)(unsigned)r.y << 21) |
+             ((unsigned long long)(unsigned)r.z << 1) | (z != 0.f ? 1ull : 0ull);
+  }
+}
+
+__global__ void k_unpack8(const unsigned long long* __restrict__ in, int64_t N, mfcd_triplet* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < N; k += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = __ldg(in + k);
+    int4 r;
+    r.x = (int)(v >> 41);
+    r.y = (int)((v >> 21) & 0xFFFFFu);
+    r.z = (int)((v >> 1) & 0xFFFFFu);
+    r.w = __float_as_int((v & 1ull) ? 1.f : 0.f);
+    reinterpret_cast<int4*>(out)[k] = r;
+  }
+}
+
 }  // namespace mfcd
 
 using namespace mfcd;
+
+extern "C" int mfcd_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t* bad, void* stream) {
+  MFCD_REQUIRE(N >= 0, "mfcd_pack_triplets8: N < 0");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(rec && out && bad, "mfcd_pack_triplets8: NULL pointer");
+  k_pack8<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(rec, N, reinterpret_cast<unsigned long long*>(out), bad);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_triplet* out, void* stream) {
+  MFCD_REQUIRE(N >= 0, "mfcd_unpack_triplets8: N < 0");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(packed && out, "mfcd_unpack_triplets8: NULL pointer");
+  k_unpack8<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(packed), N, out);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
 
 extern "C" int mfcd_abi_version(void) { return MFCD_ABI_VERSION; }
 extern "C" const char* mfcd_last_error(void) { return g_err; }

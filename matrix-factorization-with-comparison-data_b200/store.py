@@ -121,6 +121,26 @@ class TripletStore:
     def slice(self, a, b):
         return TripletStore(self.rec[a:b])
 
+    def pack8(self):
+        """-> int64 CUDA tensor of 8-byte wire records (hard labels only); raises if a record does not fit."""
+        N = len(self)
+        out = torch.empty(N, dtype=torch.int64, device=self.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.mfcd_pack_triplets8(ptr(self.rec), N, ptr(out), ptr(bad), current_stream()), "mfcd_pack_triplets8")
+        if int(bad.item()):
+            raise _lib.MfcdError("pack8: soft labels or indices beyond 2^23 users / 2^20 items do not fit the 8-byte format")
+        return out
+
+    @classmethod
+    def from_packed8(cls, packed: torch.Tensor, out_rec: torch.Tensor = None):
+        """8-byte wire records (CUDA int64) -> records; `out_rec` reuses an existing (N, 4) int32 buffer."""
+        N = packed.numel()
+        rec = torch.empty((N, 4), dtype=torch.int32, device=packed.device) if out_rec is None else out_rec
+        with torch.cuda.device(packed.device):
+            check(lib.mfcd_unpack_triplets8(ptr(packed), N, ptr(rec), current_stream()), "mfcd_unpack_triplets8")
+        return cls(rec)
+
     def hot_items(self, n_items, d, batch_size, min_hits_per_batch=2048, sample=1 << 24):
         """Item rows that would each receive >= min_hits_per_batch gradient updates per batch
         (popularity-biased sampling): candidates for K1's shared-memory privatisation.

@@ -319,6 +319,14 @@ def test_pack_unpack_gather_roundtrip(G):
     check(lib.mfcd_gather_triplets(ptr(store.rec), ptr(perm), N, ptr(out), current_stream()), "gather")
     assert torch.equal(out, store.rec[perm.long()])
     assert len(G.store_from([], [], [], [])) == 0
+    # 8-byte wire format (hard labels): exact round trip at the index limits, loud failure otherwise
+    from mfcd_b200._lib import MfcdError
+    from mfcd_b200.store import TripletStore
+    hard = G.store_from(rng.integers(0, 2 ** 23, N), rng.integers(0, 2 ** 20, N), rng.integers(0, 2 ** 20, N),
+                        rng.integers(0, 2, N).astype(np.float64))
+    assert torch.equal(TripletStore.from_packed8(hard.pack8()).rec, hard.rec)
+    with pytest.raises(MfcdError):
+        store.pack8()                      # soft labels and 31-bit user ids do not fit
 
 
 # ---- properties at BASELINE.json's full table shape (config 4: 100k x 50k, d = 64) ------------------
