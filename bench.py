@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = sized for ~15 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-format", default="all", choices=["all", "records16", "wire8", "wire_rle"])
     ap.add_argument("--bucket-mb", type=float, default=0.0,
                     help="gradient all-reduce bucket size; 0 = one all-reduce of the whole flat gradient "
                          "(measured faster than 16 MB buckets on NVLink: profiles/r01_notes.md)")
@@ -59,6 +60,8 @@ def parse():
                          "(K9); 'nccl' = NCCL all-reduce + K3")
     ap.add_argument("--multimem", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--no-hot", action="store_true", help="disable hot-row privatisation in the atomic kernel")
+    ap.add_argument("--no-group", action="store_true",
+                    help="keep the sampler's order inside a batch (default: one user's triplets adjacent)")
     return ap.parse_args()
 
 
@@ -201,6 +204,11 @@ def main():
     keys[bad] = 1
     store = sampling.btl_records(gt, sampling.TripletSet(keys, n, m), scale=1.0, K=1, soft=False, seed=seed)
     del keys, bad
+    if not args.no_group:
+        # batch layout: inside every batch one user's triplets are adjacent (same batches, same sums);
+        # done once, before the timed region, like the sampling itself
+        store.group_by_user(B)
+    k1_flags = store.k1_flags(B)
 
     torch.manual_seed(7)                           # identical replicas on every rank
     model = MatrixFactorization(n, m, d)
@@ -223,18 +231,19 @@ def main():
     n_buckets = len(mdist.bucket_bounds(numel, bucket_elems)) if world > 1 else 1
     nU = n * d
 
-    def one_step(k, rec=None, start=None, ev=None):
+    def one_step(k, rec=None, start=None, ev=None, flags=None):
         """K1 -> (all-reduce) -> K3 for global step k."""
         s, bl, bg = plan.local_range(k)
+        flags = k1_flags if flags is None else flags
         if rec is not None:
             s = start
         if ev is not None:
             ev[0].record()
         if mode == 0:
-            check(lib.mfcd_triplet_fwd_bwd_hot(ptr(fs.params), ptr(fs.params[nU:]),
-                                               ptr(rec if rec is not None else store.rec), None, s, bl, d, 1.0 / bg,
-                                               ptr(fs.grads), ptr(fs.grads[nU:]), ptr(losses[k:k + 1]), *hot_args,
-                                               current_stream()), "k1")
+            check(lib.mfcd_triplet_fwd_bwd_ex(ptr(fs.params), ptr(fs.params[nU:]),
+                                              ptr(rec if rec is not None else store.rec), None, s, bl, d, 1.0 / bg,
+                                              ptr(fs.grads), ptr(fs.grads[nU:]), ptr(losses[k:k + 1]), *hot_args,
+                                              flags, current_stream()), "k1")
         else:
             if rec is not None:
                 engine.store = TripletStore(rec)
@@ -290,52 +299,112 @@ def main():
 
     # ---- end to end: host buffers, H2D of every batch + D2H of the loss inside the timed region ---------
     e2e = None
+    e2e_formats = {}
     if not args.no_e2e:
-        # hard labels travel in the 8-byte wire format (mfcd_pack_triplets8) and are expanded on the device
-        host = torch.empty((total_steps, B), dtype=torch.int64).pin_memory()
-        host.copy_(store.pack8().view(total_steps, B).cpu())
-        wire = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
         dbuf = [torch.empty((B, 4), dtype=torch.int32, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
-        losses.zero_()
 
-        def upload(k):
-            b = k % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[b])
-                wire[b].copy_(host[k], non_blocking=True)
-                TripletStore.from_packed8(wire[b], dbuf[b])         # unpack kernel on the copy stream
-                ready[b].record(copy_stream)
+        def stage(fmt):
+            """-> (per-step pinned host tensors, per-step device staging buffers or None, unpack fn, bytes/step)"""
+            if fmt == "records16":          # the 16-byte records as they sit in HBM
+                host = torch.empty((total_steps, B, 4), dtype=torch.int32).pin_memory()
+                host.copy_(store.rec.view(total_steps, B, 4).cpu())
+                return [host[k] for k in range(total_steps)], None, None, B * 16
+            if fmt == "wire8":              # 8-byte records (hard labels)
+                host = torch.empty((total_steps, B), dtype=torch.int64).pin_memory()
+                host.copy_(store.pack8().view(total_steps, B).cpu())
+                wire = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
+                return [host[k] for k in range(total_steps)], wire, \
+                    (lambda w, out: TripletStore.from_packed8(w, out)), B * 8
+            # run-length format of a user-grouped batch: ~4.1 bytes per triplet + 4 per run
+            words = [store.pack_wire(k * B, B) for k in range(total_steps)]
+            cap = max(w.numel() for w in words)
+            host = torch.empty((total_steps, cap), dtype=torch.int32).pin_memory()
+            hk = []
+            for k, w in enumerate(words):
+                host[k, : w.numel()].copy_(w.cpu())
+                hk.append(host[k, : w.numel()])
+            wire = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
+            return hk, wire, "k1-reads-wire", sum(w.numel() for w in words) * 4 // total_steps
 
-        def run(first, count):
-            out = 0.0
-            for b in range(2):
-                freed[b].record()
-            upload(first)
-            for k in range(first, first + count):
-                if k + 1 < first + count:
-                    upload(k + 1)                   # next batch's copy overlaps this batch's compute
-                torch.cuda.current_stream().wait_event(ready[k % 2])
-                one_step(k, rec=dbuf[k % 2], start=0)
-                freed[k % 2].record()
-                out = losses[k].item()              # D2H of the step's loss (4 bytes) + sync, every step
+        def run_format(fmt):
+            host, wire, unpack, nbytes = stage(fmt)
+            # the staging loop above has just WRITTEN the pinned batches with the CPU: the last ones are still
+            # dirty in the CPU caches, and a DMA read that has to snoop them runs at ~8 GB/s instead of ~50
+            # (measured: only the last two batches of a run were slow).  Push them out to DRAM first.
+            evict = torch.empty(1 << 28, dtype=torch.int32)
+            evict.fill_(1)
+            del evict
+            direct = unpack == "k1-reads-wire"       # K1 decodes the run-length batch itself (MFCD_FLAG_WIRE_RLE)
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            freed = [torch.cuda.Event(), torch.cuda.Event()]
+            losses.zero_()
+
+            def upload(k):
+                b = k % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[b])
+                    if wire is None:
+                        dbuf[b].copy_(host[k], non_blocking=True)
+                    else:
+                        wire[b][: host[k].numel()].copy_(host[k], non_blocking=True)
+                        if not direct:
+                            unpack(wire[b], dbuf[b])                 # unpack kernel on the copy stream
+                    ready[b].record(copy_stream)
+
+            loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def run(first, count):
+                out, pending = 0.0, None
+                for b in range(2):
+                    freed[b].record()
+                upload(first)
+                for k in range(first, first + count):
+                    if k + 1 < first + count:
+                        upload(k + 1)               # next batch's copy overlaps this batch's compute
+                    torch.cuda.current_stream().wait_event(ready[k % 2])
+                    if direct:
+                        one_step(k, rec=wire[k % 2], start=0, flags=k1_flags | 2)
+                    else:
+                        one_step(k, rec=dbuf[k % 2], start=0)
+                    freed[k % 2].record()
+                    # D2H of the step's loss (4 bytes), every step; the host reads it once the NEXT step is
+                    # queued, so the GPU does not idle while python launches
+                    loss_host[k % 2: k % 2 + 1].copy_(losses[k:k + 1], non_blocking=True)
+                    done[k % 2].record()
+                    if pending is not None:
+                        done[pending % 2].synchronize()
+                        out = float(loss_host[pending % 2])
+                    pending = k
+                done[pending % 2].synchronize()
+                return float(loss_host[pending % 2])
+            run(0, W)
+            barrier()
+            w0 = time.perf_counter()
+            last = run(W, K)
+            barrier()
+            w1 = time.perf_counter()
+            te = torch.tensor([w1 - w0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            out = {"value": world * B * K / float(te[0]), "unit": "triplets/s",
+                   "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": world * 4, "last_loss": last}
             return out
-        run(0, W)
-        barrier()
-        w0 = time.perf_counter()
-        last = run(W, K)
-        barrier()
-        w1 = time.perf_counter()
-        te = torch.tensor([w1 - w0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * K / float(te[0]), "unit": "triplets/s",
-               "h2d_bytes_per_step": world * B * 8, "d2h_bytes_per_step": world * 4,
-               "how": "pinned host records in the 8-byte wire format -> cudaMemcpyAsync + unpack kernel (double-buffered "
-                      "on a copy stream) -> K1 -> exchange -> update -> loss.item() each step; wall clock, max over ranks",
-               "last_loss": last}
+
+        formats = ["records16", "wire8"] + (["wire_rle"] if (k1_flags and m <= 65536 and mode == 0 and d % 4 == 0) else [])
+        for fmt in (formats if args.e2e_format == "all" else [args.e2e_format]):
+            e2e_formats[fmt] = run_format(fmt)
+        best = "wire_rle" if "wire_rle" in e2e_formats else ("wire8" if "wire8" in e2e_formats else list(e2e_formats)[0])
+        e2e = dict(e2e_formats[best])
+        e2e["format"] = best
+        e2e["how"] = ("pinned host batches in the '%s' staging format -> cudaMemcpyAsync + unpack kernel (double-buffered "
+                      "on a copy stream) -> K1 -> exchange -> update -> loss.item() each step; wall clock, max over "
+                      "ranks. records16 = the 16-byte HBM records; wire8 = 8-byte hard-label records; wire_rle = "
+                      "run-length format of a user-grouped batch, decoded by K1 itself (include/mfcd_b200.h: mfcd_pack_wire, "
+                      "MFCD_FLAG_WIRE_RLE)" % best)
+        e2e["other_formats"] = {f: {"value": v["value"], "h2d_bytes_per_step": v["h2d_bytes_per_step"]}
+                                for f, v in e2e_formats.items() if f != best}
 
     # ---- CPU baseline (rank 0, N == 1 only) -------------------------------------------------------------
     cpu = None
@@ -378,6 +447,7 @@ def main():
                        "dp_exchange": ("none" if world == 1 else ("peer-memory fused K9" + (" (multimem)" if exchange.multimem else " (p2p)")
                                                                   if exchange is not None else "nccl all-reduce + K3")),
                        "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
+                       "batch_layout": ("grouped by user inside each batch" if k1_flags else "sampler order"),
                        "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB) are L2-resident "
                                     "by design of the algorithm"},
             "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,

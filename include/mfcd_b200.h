@@ -74,6 +74,18 @@ int mfcd_unpack_triplets(const mfcd_triplet* rec, int64_t N, int64_t* u, int64_t
  * pack sets *bad (device int, caller zeroes it) if a record has a soft label or an index out of range. */
 int mfcd_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t* bad, void* stream);
 int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_triplet* out, void* stream);
+/* Run-length wire format for ONE user-grouped batch of B hard-labelled records with n_items <= 65536
+ * (4.375 bytes per triplet + 4 per run of equal users instead of 16): u32 words
+ *   [n_runs, B, 0, 0 | word_run0[nw] | zbits[nw] | nbits[nw] | ij[B] | users[n_runs]],  nw = ceil(B/32);
+ *   word_run0[w] = run starts before triplet 32 w, nbits = run-start bits, ij = i | j << 16;
+ *   `fixed_words` = words before users[], `capacity_words` = fixed_words + B (worst case).
+ * pack: device records -> device wire (word 0 = n_runs tells how many words to ship: fixed_words + n_runs);
+ * sets *bad (caller zeroes it) for soft labels or items >= 65536.  unpack: device wire -> device records,
+ * the per-step side of host staging (structure.py:846 `x.to(device)` moved 32 bytes per sample). */
+int mfcd_wire_layout(int64_t B, int64_t* fixed_words, int64_t* capacity_words, size_t* workspace_bytes);
+int mfcd_pack_wire(const mfcd_triplet* rec, int64_t B, uint32_t* wire, int64_t capacity_words, int32_t* bad,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int mfcd_unpack_wire(const uint32_t* wire, int64_t B, mfcd_triplet* out, void* stream);
 /* out[k] = rec[perm[k]] for k in [0,N): materialise one epoch's shuffled order
  * (replaces RandomSampler + default_collate, structure.py:738, :845). */
 int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N, mfcd_triplet* out,
@@ -101,6 +113,30 @@ int mfcd_triplet_fwd_bwd_hot(const float* U, const float* V, const mfcd_triplet*
                              int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
                              float* loss, const int8_t* item_slot, const int32_t* hot_items, int32_t n_hot,
                              void* stream);
+
+/* General form of the atomic-mode K1: hot rows optional (NULL / 0), plus `flags`:
+ *   MFCD_FLAG_USER_GROUPED  the batch keeps each user's triplets adjacent (see mfcd_group_by_user) and perm
+ *                           is NULL: U[u] is then read once and its gradient row leaves as one reduction per
+ *                           run of equal u instead of one per triplet.  The flag is a hint: results are
+ *                           correct for any order (same sums, different fp32 summation order).
+ *   MFCD_FLAG_WIRE_RLE      `rec` is not an array of records but ONE batch in the run-length wire format
+ *                           (mfcd_pack_wire; start = 0, perm = NULL, B = its size): K1 decodes it on the fly,
+ *                           so a batch staged from the host needs no unpack pass.  d must be a multiple of
+ *                           4 that the float4 lane groups cover exactly (4..128, 256, 384, 512). */
+#define MFCD_FLAG_USER_GROUPED 1
+#define MFCD_FLAG_WIRE_RLE 2
+int mfcd_triplet_fwd_bwd_ex(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                            int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
+                            float* loss, const int8_t* item_slot, const int32_t* hot_items, int32_t n_hot,
+                            int32_t flags, void* stream);
+
+/* Reorders rec[0..N) in place so that inside every batch of batch_size consecutive records the triplets
+ * of one user are adjacent (stable).  Batch membership is unchanged, so a training step over a batch is
+ * the same sum in a different order -- the reference draws batches from a shuffled DataLoader
+ * (structure.py:738) and never depends on the order inside one.  Workspace: see the query function. */
+int mfcd_group_by_user_workspace(int64_t N, int64_t batch_size, size_t* bytes);
+int mfcd_group_by_user(mfcd_triplet* rec, int64_t N, int64_t batch_size, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* ---- K1+K2: deterministic variant ------------------------------------------
  * Same contract, but run-to-run bit-reproducible: per-row gradient sums are
@@ -162,7 +198,7 @@ typedef struct mfcd_epoch_args {
   int32_t d;
   int32_t optimizer;
   int32_t mode;
-  int32_t reserved;
+  int32_t flags;             /* MFCD_FLAG_* (atomic mode) */
   const mfcd_triplet* rec;
   const int32_t* perm; /* epoch order, length n_samples, or NULL */
   int64_t n_samples;

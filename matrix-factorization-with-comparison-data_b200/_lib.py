@@ -32,7 +32,7 @@ class EpochArgs(C.Structure):
     _fields_ = [
         ("params", C.c_void_p), ("grads", C.c_void_p), ("state1", C.c_void_p), ("state2", C.c_void_p),
         ("n_users", C.c_int64), ("n_items", C.c_int64),
-        ("d", C.c_int32), ("optimizer", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32),
+        ("d", C.c_int32), ("optimizer", C.c_int32), ("mode", C.c_int32), ("flags", C.c_int32),
         ("rec", C.c_void_p), ("perm", C.c_void_p),
         ("n_samples", C.c_int64), ("batch_size", C.c_int64),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
@@ -58,10 +58,16 @@ SIGNATURES = {
     "mfcd_unpack_triplets": [P, I64, P, P, P, P, P],
     "mfcd_pack_triplets8": [P, I64, P, P, P],
     "mfcd_unpack_triplets8": [P, I64, P, P],
+    "mfcd_wire_layout": [I64, C.POINTER(I64), C.POINTER(I64), C.POINTER(SZ)],
+    "mfcd_pack_wire": [P, I64, P, I64, P, P, SZ, P],
+    "mfcd_unpack_wire": [P, I64, P, P],
     "mfcd_gather_triplets": [P, P, I64, P, P],
     "mfcd_triplet_fwd_bwd": [P, P, P, P, I64, I64, I32, F32, P, P, P, P],
     "mfcd_max_hot_items": [I32, C.POINTER(I32)],
     "mfcd_triplet_fwd_bwd_hot": [P, P, P, P, I64, I64, I32, F32, P, P, P, P, P, I32, P],
+    "mfcd_triplet_fwd_bwd_ex": [P, P, P, P, I64, I64, I32, F32, P, P, P, P, P, I32, I32, P],
+    "mfcd_group_by_user_workspace": [I64, I64, C.POINTER(SZ)],
+    "mfcd_group_by_user": [P, I64, I64, P, SZ, P],
     "mfcd_det_workspace_bytes": [I64, I32, C.POINTER(SZ)],
     "mfcd_triplet_fwd_bwd_det": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
     "mfcd_adam_update": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, I32, P],
@@ -118,6 +124,8 @@ def _load():
 
 lib = _load()
 ABI_VERSION = lib.mfcd_abi_version()
+FLAG_USER_GROUPED = 1      # MFCD_FLAG_USER_GROUPED
+FLAG_WIRE_RLE = 2          # MFCD_FLAG_WIRE_RLE
 
 
 def check(rc: int, what: str = "") -> None:

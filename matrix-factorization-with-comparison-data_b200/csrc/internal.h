@@ -10,7 +10,7 @@ int launch_sgd(float* p, float* g, float* buf, int64_t numel, float lr, float mo
 int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                           int64_t start, int64_t B, int d, float inv_batch, float* gU, float* gV,
                           float* loss, const int8_t* item_slot, const int32_t* hot_items, int n_hot,
-                          cudaStream_t st);
+                          int flags, cudaStream_t st);
 int max_hot_rows(int d);
 int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                        int64_t start, int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items,

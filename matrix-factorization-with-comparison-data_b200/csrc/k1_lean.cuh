@@ -1,0 +1,366 @@
+// K1 lean: the atomic-mode fused forward + BCE + backward kernel for rows that exactly fill their lane
+// group with float4 fragments (d == 4*LPT*NITER: d = 4, 8, 16, 32, 64, 128, 256, 384, 512).
+// Same arithmetic as k_fwd_bwd<..., MODE 0> (structure.py:787-795, :849-850), restructured after the ncu
+// profiles of that kernel (profiles/r01b_*):
+//
+//   * issue slots (103 warp instructions per triplet, 68 % issue-active on zipf items): D is a compile-time
+//     constant, the score gradient is g = (p - z)/B with the reference's saturation branch (p(1-p) < 1e-12)
+//     kept as a rare slow path and p = rcp.approx(1 + expf(-x)), so no IEEE division sequences run per lane
+//     group (the REPORTED loss still uses the exact sigmoid / BCE, once per tile, SIMD over the home lanes);
+//   * hot item rows: one shared-memory image per warp as before, but the lane groups of a warp simply take
+//     turns in program order (SHARE) -- the clash detection, votes and __syncwarp of k_fwd_bwd are gone; an
+//     image per lane group (MFCD_K1_SHARE=0) costs twice the shared memory per row and measured slower;
+//   * RUNS: on uniform items the kernel is bound by the L1 -> crossbar request port (82 % busy: every row
+//     read that misses L1 and every RED is a request).  When the batch keeps each user's triplets adjacent
+//     (mfcd_group_by_user), the U row is read once and its gradient leaves as ONE reduction per run instead
+//     of once per triplet: a third of the requests disappear.  Correct for any order, faster when grouped.
+#pragma once
+#include "shape_dispatch.cuh"
+
+namespace mfcd {
+
+// read-modify-write of a lane's fragment in shared memory, addressed by a 32-bit shared-window address
+__device__ __forceinline__ void smem_add4_at(uint32_t addr, const Frag<4>& f) {
+  float4 t;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
+  t.x += f.v[0]; t.y += f.v[1]; t.z += f.v[2]; t.w += f.v[3];
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float p;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(1.f + expf(-x)));
+  return p;
+}
+
+// (p - z)/B; the reference's value (0, or its clamped form) where p(1-p) underflows 1e-12
+__device__ __forceinline__ float bce_grad_score_fast(float p, float z, float inv_batch) {
+  const float omp = 1.f - p;
+  const float q = omp * p;
+  float g = inv_batch * (p - z);
+  if (q < 1e-12f) g = g * 1e12f * omp * p;
+  return g;
+}
+
+constexpr int kLeanBlock = 256;
+
+// CTAs per SM the register budget is sized for
+template <int NITER, bool HOT, bool SHARE>
+constexpr int lean_min_blocks() {
+  return NITER > 2 ? 1 : (HOT ? (SHARE ? 3 : 2) : (NITER == 2 ? 3 : 4));
+}
+
+// SHARE: the lane groups of a warp share ONE hot image (half the shared memory per row at d = 64) and take
+// turns updating it, group after group, in program order -- no detection, no barrier.
+// WIRE: `rec` is one user-grouped batch in the run-length staging format of wire.cu (start = 0, perm = NULL):
+// the step then needs no unpack pass between the host-to-device copy and K1.
+template <int LPT, int NITER, bool HOT, bool RUNS, bool SHARE, bool WIRE = false>
+__global__ void __launch_bounds__(kLeanBlock, lean_min_blocks<NITER, HOT, SHARE>())
+k_fwd_bwd_lean(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
+               const int32_t* __restrict__ perm, int64_t start, int64_t B, float inv_batch,
+               float* __restrict__ gU, float* __restrict__ gV, float* __restrict__ loss_out,
+               const int8_t* __restrict__ item_slot, const int32_t* __restrict__ hot_items, int n_hot) {
+  constexpr int VEC = 4;
+  constexpr int D = VEC * LPT * NITER;                 // floats per row
+  constexpr uint32_t ROWB = D * 4;                     // bytes per row
+  constexpr int STEP = LPT * VEC * 4;                  // bytes between a lane's NITER fragments
+  constexpr int UNR = LPT >= 2 ? 2 : 1;                // triplets in flight per lane group (4 was measured: no gain)
+  constexpr int GPW = 32 / LPT;                        // lane groups per warp
+  constexpr int IMAGES = SHARE ? kLeanBlock / 32 : kLeanBlock / LPT;   // hot images per CTA
+  constexpr uint32_t NO_USER = 0xffffffffu;
+  __shared__ float s_red[kLeanBlock / 32];
+  extern __shared__ __align__(16) float s_hot[];       // HOT: [IMAGES][n_hot][D]
+  if constexpr (HOT) {
+    for (int e = threadIdx.x; e < IMAGES * n_hot * D; e += kLeanBlock) s_hot[e] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+  // row r of a table starts at base + r * ROWB; the lane's fragment sits lane_off bytes into the row
+  const uint64_t lane_off = (uint64_t)(sub * (VEC * 4));
+  const char* Ub = reinterpret_cast<const char*>(U);
+  const char* Vb = reinterpret_cast<const char*>(V);
+  char* gUb = reinterpret_cast<char*>(gU);
+  char* gVb = reinterpret_cast<char*>(gV);
+  // this lane's column of its image, as a shared-window address
+  const uint32_t my_hot = (uint32_t)__cvta_generic_to_shared(s_hot) +
+                          (uint32_t)(threadIdx.x / (SHARE ? 32 : LPT)) * (uint32_t)n_hot * ROWB + sub * (VEC * 4);
+
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float loss_acc = 0.f;
+  for (int64_t base = warp0 * 32; base < B; base += nwarps * 32) {
+    const int64_t k = base + lane;
+    int4 r = make_int4(0, 0, 0, 0);
+    int slots = 0xffff;                                // (slot_i & 0xff) | (slot_j & 0xff) << 8, 0xff = cold
+    if (k < B) {
+      if constexpr (WIRE) {
+        const uint32_t* wire = reinterpret_cast<const uint32_t*>(rec);
+        const int64_t nw = (B + 31) >> 5, w = base >> 5;           // [hdr 4 | run0 nw | zbits nw | nbits nw | ij B | users]
+        const uint32_t bits = __ldg(wire + 4 + 2 * nw + w);
+        const uint32_t zw = __ldg(wire + 4 + nw + w);
+        const uint32_t ij = __ldg(wire + 4 + 3 * nw + k);
+        const uint32_t run = __ldg(wire + 4 + w) + __popc(bits & (0xffffffffu >> (31 - lane))) - 1u;
+        r.x = (int)__ldg(wire + 4 + 3 * nw + B + run);
+        r.y = (int)(ij & 0xffffu);
+        r.z = (int)(ij >> 16);
+        r.w = __float_as_int(((zw >> lane) & 1u) ? 1.f : 0.f);
+      } else {
+        const int64_t idx = perm ? (int64_t)__ldg(perm + start + k) : (start + k);
+        r = __ldg(reinterpret_cast<const int4*>(rec) + idx);
+      }
+      if constexpr (HOT)
+        slots = ((int)__ldg(item_slot + r.y) & 0xff) | (((int)__ldg(item_slot + r.z) & 0xff) << 8);
+    }
+    const int nvalid = (B - base) < 32 ? (int)(B - base) : 32;
+    float x_home = 0.f;
+    // RUNS: the user row in flight and its gradient, carried across this group's LPT slots of the tile
+    uint32_t cur_u = NO_USER;
+    Frag<VEC> cu[NITER], accU[NITER];
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) { cu[it] = frag_zero<VEC>(); accU[it] = frag_zero<VEC>(); }
+
+#pragma unroll 1
+    for (int r0 = 0; r0 < LPT; r0 += UNR) {
+      Frag<VEC> uu[UNR][NITER], dv[UNR][NITER];
+      uint32_t tu[UNR], ti[UNR], tj[UNR];
+      int ts[UNR];
+      float tz[UNR];
+      bool fresh[UNR];                                 // RUNS: this triplet starts a new user run
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int e = grp * LPT + r0 + q;              // tile slot this group handles in this round
+        tu[q] = (uint32_t)__shfl_sync(0xffffffffu, r.x, e);
+        ti[q] = (uint32_t)__shfl_sync(0xffffffffu, r.y, e);
+        tj[q] = (uint32_t)__shfl_sync(0xffffffffu, r.z, e);
+        tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+        ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
+        if constexpr (RUNS) {
+          if (e >= nvalid) tu[q] = (q == 0) ? cur_u : tu[q > 0 ? q - 1 : 0];   // padding never opens a run
+          fresh[q] = tu[q] != ((q == 0) ? cur_u : tu[q > 0 ? q - 1 : 0]);
+        } else {
+          fresh[q] = true;
+        }
+        const char* pu = Ub + ((uint64_t)tu[q] * ROWB + lane_off);
+        const char* pi = Vb + ((uint64_t)ti[q] * ROWB + lane_off);
+        const char* pj = Vb + ((uint64_t)tj[q] * ROWB + lane_off);
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          if (fresh[q] && (!RUNS || tu[q] != NO_USER))
+            uu[q][it] = ldg_frag<VEC>(reinterpret_cast<const float*>(pu + it * STEP));
+          const Frag<VEC> a = ldg_frag<VEC>(reinterpret_cast<const float*>(pi + it * STEP));
+          const Frag<VEC> b = ldg_frag<VEC>(reinterpret_cast<const float*>(pj + it * STEP));
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) dv[q][it].v[kk] = a.v[kk] - b.v[kk];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const bool ok = grp * LPT + r0 + q < nvalid;   // false only in the last, partial tile
+        if constexpr (RUNS) {
+          if (fresh[q]) {
+            if (cur_u != NO_USER) {                    // close the previous run: one reduction per row
+              char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+#pragma unroll
+              for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+            }
+#pragma unroll
+            for (int it = 0; it < NITER; ++it) { accU[it] = frag_zero<VEC>(); cu[it] = uu[q][it]; }
+            cur_u = tu[q];
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) cu[it] = uu[q][it];
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it)
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) part = fmaf(cu[it].v[kk], dv[q][it].v[kk], part);
+        const float x = group_sum<LPT>(part, 0xffffffffu);
+        x_home = (sub == r0 + q) ? x : x_home;
+        float g = bce_grad_score_fast(sigmoid_fast(x), tz[q], inv_batch);
+        if (!ok) g = 0.f;
+        const float ng = -g;
+        const int si = ts[q] & 0xff, sj = ts[q] >> 8;
+        const bool cold_i = !HOT || si == 0xff;
+        const bool cold_j = !HOT || sj == 0xff;
+        if constexpr (RUNS) {
+#pragma unroll
+          for (int it = 0; it < NITER; ++it)
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) accU[it].v[kk] = fmaf(g, dv[q][it].v[kk], accU[it].v[kk]);
+        }
+        if (ok) {
+          char* di = gVb + ((uint64_t)ti[q] * ROWB + lane_off);
+          char* dj = gVb + ((uint64_t)tj[q] * ROWB + lane_off);
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) {
+            Frag<VEC> b, nb;
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) {
+              b.v[kk] = g * cu[it].v[kk];
+              nb.v[kk] = ng * cu[it].v[kk];
+            }
+            if constexpr (!RUNS) {
+              Frag<VEC> a;
+#pragma unroll
+              for (int kk = 0; kk < VEC; ++kk) a.v[kk] = g * dv[q][it].v[kk];
+              char* du = gUb + ((uint64_t)tu[q] * ROWB + lane_off);
+              red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), a);
+            }
+            if (cold_i) red_frag<VEC>(reinterpret_cast<float*>(di + it * STEP), b);
+            if (cold_j) red_frag<VEC>(reinterpret_cast<float*>(dj + it * STEP), nb);
+            if constexpr (HOT && !SHARE) {
+              // this group's own image: no other lane touches these 16 bytes, program order is enough
+              if (!cold_i) smem_add4_at(my_hot + si * ROWB + it * STEP, b);
+              if (!cold_j) smem_add4_at(my_hot + sj * ROWB + it * STEP, nb);
+            }
+          }
+        }
+        if constexpr (HOT && SHARE) {
+          // one image per warp: its lane groups update it one after the other (same-warp shared-memory
+          // accesses complete in program order, so group 1's read sees group 0's write)
+#pragma unroll
+          for (int ph = 0; ph < GPW; ++ph) {
+            if (grp == ph && ok) {
+#pragma unroll
+              for (int it = 0; it < NITER; ++it) {
+                Frag<VEC> b, nb;
+#pragma unroll
+                for (int kk = 0; kk < VEC; ++kk) {
+                  b.v[kk] = g * cu[it].v[kk];
+                  nb.v[kk] = ng * cu[it].v[kk];
+                }
+                if (!cold_i) smem_add4_at(my_hot + si * ROWB + it * STEP, b);
+                if (!cold_j) smem_add4_at(my_hot + sj * ROWB + it * STEP, nb);
+              }
+            }
+          }
+        }
+      }
+    }
+    if constexpr (RUNS) {
+      if (cur_u != NO_USER) {                          // the run still open at the end of the tile
+        char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+      }
+    }
+    // the tile's losses, one triplet per lane (exact sigmoid / BCE: this is the reported number)
+    if (lane < nvalid) loss_acc += bce_ref(sigmoidf_ref(x_home), __int_as_float(r.w));
+  }
+
+  if constexpr (HOT) {
+    // one reduction per privatised row element and CTA
+    __syncthreads();
+    const int per_img = n_hot * D;
+    for (int e = threadIdx.x; e < per_img; e += kLeanBlock) {
+      float t = 0.f;
+#pragma unroll 4
+      for (int w = 0; w < IMAGES; ++w) t += s_hot[w * per_img + e];
+      if (t != 0.f) atomicAdd(gV + (int64_t)__ldg(hot_items + e / D) * D + (e % D), t);
+    }
+  }
+  // block loss: warp sums -> warp 0
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) s_red[threadIdx.x >> 5] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (lane < kLeanBlock / 32) ? s_red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(loss_out, t * inv_batch);
+  }
+}
+
+// shared memory one hot row costs in the lean kernel: an image per lane group, or per warp (SHARE)
+static inline bool lean_share() {
+  static const bool on = !(getenv("MFCD_K1_SHARE") && atoi(getenv("MFCD_K1_SHARE")) == 0);
+  return on;
+}
+static inline size_t lean_hot_row_bytes(int lpt, int niter) {
+  const int images = lean_share() ? kLeanBlock / 32 : kLeanBlock / lpt;
+  return (size_t)images * 4 * lpt * niter * sizeof(float);
+}
+static inline int hot_smem_budget() {
+  static const int kb = getenv("MFCD_HOT_SMEM_KB") ? atoi(getenv("MFCD_HOT_SMEM_KB")) : 64;
+  return kb * 1024;
+}
+static inline bool lean_enabled() {
+  static const bool on = !(getenv("MFCD_K1_LEAN") && atoi(getenv("MFCD_K1_LEAN")) == 0);
+  return on;
+}
+// d that the lean kernel covers: float4 fragments that exactly fill the lane group
+static inline bool lean_shape(int d, const RowShape& s) { return s.vec == 4 && d == 4 * s.lpt * s.niter; }
+
+template <int LPT, int NITER, bool HOT, bool RUNS, bool SHARE, bool WIRE = false>
+static int launch_lean_kernel(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                              int64_t start, int64_t B, float inv_batch, float* gU, float* gV, float* loss,
+                              const int8_t* item_slot, const int32_t* hot_items, int n_hot, size_t smem,
+                              cudaStream_t st) {
+  auto kern = k_fwd_bwd_lean<LPT, NITER, HOT, RUNS, SHARE, WIRE>;
+  constexpr int want = lean_min_blocks<NITER, HOT, SHARE>();
+  int per_sm = want;
+  if (HOT) {
+    if (smem > 40 * 1024)   // opt-in above the default 48 KB (static + dynamic) limit; per device, so not cached
+      MFCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fit = (int)((227 * 1024) / (smem + 1024));
+    per_sm = fit < want ? (fit < 1 ? 1 : fit) : want;
+  }
+  // HOT: long-lived CTAs (few flushes per hot row); otherwise a block pass covers 8 warp tiles of 32 triplets
+  const int grid = grid_for(B, HOT ? kLeanBlock * 8 : kLeanBlock, per_sm);
+  kern<<<grid, kLeanBlock, smem, st>>>(U, V, rec, perm, start, B, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+template <int LPT, int NITER>
+static int launch_lean(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                       int64_t B, float inv_batch, float* gU, float* gV, float* loss, const int8_t* item_slot,
+                       const int32_t* hot_items, int n_hot, bool runs, bool wire, cudaStream_t st) {
+#define MFCD_LEAN_GO(HOT, RUNS, SHARE, WIRE)                                                              \
+  return launch_lean_kernel<LPT, NITER, HOT, RUNS, SHARE, WIRE>(U, V, rec, perm, start, B, inv_batch, gU, gV, \
+                                                                loss, item_slot, hot_items, n_hot, smem, st)
+  if (n_hot > 0) {
+    const size_t smem = lean_hot_row_bytes(LPT, NITER) * n_hot;
+    if constexpr (LPT < 32) {
+      if (lean_share()) {
+        if (wire) MFCD_LEAN_GO(true, true, true, true);
+        if (runs) MFCD_LEAN_GO(true, true, true, false); else MFCD_LEAN_GO(true, false, true, false);
+      }
+    }
+    if (wire) MFCD_LEAN_GO(true, true, false, true);
+    if (runs) MFCD_LEAN_GO(true, true, false, false); else MFCD_LEAN_GO(true, false, false, false);
+  } else {
+    const size_t smem = 0;
+    if (wire) MFCD_LEAN_GO(false, true, false, true);
+    if (runs) MFCD_LEAN_GO(false, true, false, false); else MFCD_LEAN_GO(false, false, false, false);
+  }
+#undef MFCD_LEAN_GO
+}
+
+static int dispatch_lean(const RowShape& s, const float* U, const float* V, const mfcd_triplet* rec,
+                         const int32_t* perm, int64_t start, int64_t B, float inv_batch, float* gU, float* gV,
+                         float* loss, const int8_t* item_slot, const int32_t* hot_items, int n_hot, bool runs,
+                         bool wire, cudaStream_t st) {
+#define MFCD_LEAN_CASE(L, N) \
+  return launch_lean<L, N>(U, V, rec, perm, start, B, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot, runs, wire, st)
+  switch (s.lpt) {
+    case 1: MFCD_LEAN_CASE(1, 1);
+    case 2: MFCD_LEAN_CASE(2, 1);
+    case 4: MFCD_LEAN_CASE(4, 1);
+    case 8: MFCD_LEAN_CASE(8, 1);
+    case 16: MFCD_LEAN_CASE(16, 1);
+    default:
+      switch (s.niter) {
+        case 1: MFCD_LEAN_CASE(32, 1);
+        case 2: MFCD_LEAN_CASE(32, 2);
+        case 3: MFCD_LEAN_CASE(32, 3);
+        default: MFCD_LEAN_CASE(32, 4);
+      }
+  }
+#undef MFCD_LEAN_CASE
+}
+
+}  // namespace mfcd

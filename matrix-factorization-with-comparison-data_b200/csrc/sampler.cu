@@ -360,3 +360,98 @@ extern "C" int mfcd_philox_uniforms(uint64_t seed, uint64_t w0, int64_t count, f
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Batch layout for K1's RUNS mode: inside every batch of `batch_size` consecutive records, bring the
+// triplets of one user together (stable: a user's triplets keep their relative order).  Which triplets a
+// batch holds does not change, so the optimiser step is the same sum in a different order.
+// One stable radix sort (cub, library) of (batch index << 32 | user) keys per chunk of whole batches.
+// ---------------------------------------------------------------------------
+namespace mfcd {
+constexpr int64_t kGroupChunk = int64_t(1) << 25;
+
+struct GroupLayout {
+  size_t k_in, k_out, i_in, i_out, tmp, cub_temp, total, cub_bytes;
+  int64_t chunk;
+};
+
+static GroupLayout group_layout(int64_t N, int64_t batch) {
+  GroupLayout L;
+  int64_t chunk = batch >= kGroupChunk ? batch : (kGroupChunk / batch) * batch;
+  if (chunk > N) chunk = N;
+  L.chunk = chunk;
+  auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t off = 0;
+  L.k_in = off; off += up(sizeof(uint64_t) * chunk);
+  L.k_out = off; off += up(sizeof(uint64_t) * chunk);
+  L.i_in = off; off += up(sizeof(uint32_t) * chunk);
+  L.i_out = off; off += up(sizeof(uint32_t) * chunk);
+  L.tmp = off; off += up(sizeof(mfcd_triplet) * chunk);
+  size_t cb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cb, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, chunk, 0, 64);
+  L.cub_bytes = cb;
+  L.cub_temp = off; off += up(cb);
+  L.total = off;
+  return L;
+}
+
+__global__ void __launch_bounds__(256)
+k_group_keys(const mfcd_triplet* __restrict__ rec, int64_t count, int64_t batch, uint64_t* __restrict__ keys,
+             uint32_t* __restrict__ idx) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+    keys[k] = ((uint64_t)(k / batch) << 32) | (uint32_t)__ldg(&rec[k].u);
+    idx[k] = (uint32_t)k;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_group_gather(const mfcd_triplet* __restrict__ rec, const uint32_t* __restrict__ idx, int64_t count,
+               mfcd_triplet* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x)
+    reinterpret_cast<int4*>(out)[k] = __ldg(reinterpret_cast<const int4*>(rec) + idx[k]);
+}
+}  // namespace mfcd
+
+extern "C" int mfcd_group_by_user_workspace(int64_t N, int64_t batch_size, size_t* bytes) {
+  MFCD_REQUIRE(bytes != nullptr && N >= 0 && batch_size >= 1, "mfcd_group_by_user_workspace: bad argument");
+  *bytes = N == 0 ? 0 : mfcd::group_layout(N, batch_size).total;
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_group_by_user(mfcd_triplet* rec, int64_t N, int64_t batch_size, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  using namespace mfcd;
+  MFCD_REQUIRE(N >= 0 && batch_size >= 1, "mfcd_group_by_user: bad sizes");
+  if (N == 0) return MFCD_OK;
+  MFCD_REQUIRE(rec != nullptr, "mfcd_group_by_user: rec is NULL");
+  MFCD_REQUIRE(batch_size < (int64_t(1) << 32), "mfcd_group_by_user: batch too large");
+  const GroupLayout L = group_layout(N, batch_size);
+  if (workspace == nullptr || workspace_bytes < L.total) {
+    set_error("mfcd_group_by_user: workspace too small (%zu < %zu bytes)", workspace_bytes, L.total);
+    return MFCD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* base = static_cast<char*>(workspace);
+  uint64_t* k_in = reinterpret_cast<uint64_t*>(base + L.k_in);
+  uint64_t* k_out = reinterpret_cast<uint64_t*>(base + L.k_out);
+  uint32_t* i_in = reinterpret_cast<uint32_t*>(base + L.i_in);
+  uint32_t* i_out = reinterpret_cast<uint32_t*>(base + L.i_out);
+  mfcd_triplet* tmp = reinterpret_cast<mfcd_triplet*>(base + L.tmp);
+  for (int64_t c0 = 0; c0 < N; c0 += L.chunk) {
+    const int64_t count = (N - c0) < L.chunk ? (N - c0) : L.chunk;
+    const int64_t nb = (count + batch_size - 1) / batch_size;
+    int hi_bits = 0;
+    while ((int64_t(1) << hi_bits) < nb) ++hi_bits;
+    const int grid = grid_for(count, 256, 8);
+    k_group_keys<<<grid, 256, 0, st>>>(rec + c0, count, batch_size, k_in, i_in);
+    MFCD_CHECK_LAUNCH();
+    size_t cb = L.cub_bytes;
+    MFCD_CUDA(cub::DeviceRadixSort::SortPairs(base + L.cub_temp, cb, (const uint64_t*)k_in, k_out,
+                                              (const uint32_t*)i_in, i_out, count, 0, 32 + hi_bits, st));
+    k_group_gather<<<grid, 256, 0, st>>>(rec + c0, i_out, count, tmp);
+    MFCD_CHECK_LAUNCH();
+    MFCD_CUDA(cudaMemcpyAsync(rec + c0, tmp, sizeof(mfcd_triplet) * count, cudaMemcpyDeviceToDevice, st));
+  }
+  return MFCD_OK;
+}

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "internal.h"
 #include "shape_dispatch.cuh"
+#include "k1_lean.cuh"
 
 namespace mfcd {
 
@@ -293,20 +294,40 @@ struct AtomicLauncher {
 int max_hot_rows(int d) {
   // 64 KB of shared memory for the 8 per-warp images; slots are int8 (<= 127)
   RowShape s;
-  if (!row_shape_for(d, &s) || s.lpt < 8) return 0;
-  static const int budget_kb = getenv("MFCD_HOT_SMEM_KB") ? atoi(getenv("MFCD_HOT_SMEM_KB")) : 64;
-  int h = (budget_kb * 1024) / ((kBlock / 32) * d * (int)sizeof(float));
+  if (!row_shape_for(d, &s)) return 0;
+  int h;
+  if (lean_shape(d, s) && lean_enabled())     // lean kernel: an image per lane group
+    h = hot_smem_budget() / (int)lean_hot_row_bytes(s.lpt, s.niter);
+  else if (s.lpt < 8) return 0;
+  else {
+    static const int budget_kb = getenv("MFCD_HOT_SMEM_KB") ? atoi(getenv("MFCD_HOT_SMEM_KB")) : 64;
+    h = (budget_kb * 1024) / ((kBlock / 32) * d * (int)sizeof(float));
+  }
   return h > 127 ? 127 : h;
 }
 
 int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                           int64_t start, int64_t B, int d, float inv_batch, float* gU, float* gV, float* loss,
-                          const int8_t* item_slot, const int32_t* hot_items, int n_hot, cudaStream_t st) {
+                          const int8_t* item_slot, const int32_t* hot_items, int n_hot, int flags,
+                          cudaStream_t st) {
   if (B == 0) return MFCD_OK;
   HotRows hot{item_slot, hot_items, (item_slot && hot_items) ? n_hot : 0};
   if (hot.n_hot > max_hot_rows(d)) {
     set_error("too many hot rows for d=%d: %d > %d", d, hot.n_hot, max_hot_rows(d));
     return MFCD_ERR_ARG;
+  }
+  RowShape shape_l;
+  const bool wire = (flags & MFCD_FLAG_WIRE_RLE) != 0;
+  if (wire && (perm != nullptr || start != 0)) {
+    set_error("MFCD_FLAG_WIRE_RLE: the wire batch is read whole (start = 0, perm = NULL)");
+    return MFCD_ERR_ARG;
+  }
+  if (row_shape_for(d, &shape_l) && lean_shape(d, shape_l) && (lean_enabled() || wire))
+    return dispatch_lean(shape_l, U, V, rec, perm, start, B, inv_batch, gU, gV, loss, hot.item_slot, hot.hot_items,
+                         hot.n_hot, (flags & MFCD_FLAG_USER_GROUPED) != 0 && perm == nullptr, wire, st);
+  if (wire) {
+    set_error("MFCD_FLAG_WIRE_RLE needs d in {4, 8, 16, 32, 64, 128, 256, 384, 512}; unpack the batch first (d=%d)", d);
+    return MFCD_ERR_UNSUPPORTED;
   }
   MFCD_DISPATCH_ROW_SHAPE(AtomicLauncher, d, U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, hot, st);
 }
@@ -599,7 +620,7 @@ extern "C" int mfcd_triplet_fwd_bwd(const float* U, const float* V, const mfcd_t
                                     float* loss, void* stream) {
   int rc = check_common("mfcd_triplet_fwd_bwd", U, V, rec, start, B, d, gU, gV, loss);
   if (rc != MFCD_OK) return rc;
-  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, nullptr, nullptr, 0,
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, nullptr, nullptr, 0, 0,
                                as_stream(stream));
 }
 
@@ -616,8 +637,19 @@ extern "C" int mfcd_triplet_fwd_bwd_hot(const float* U, const float* V, const mf
   int rc = check_common("mfcd_triplet_fwd_bwd_hot", U, V, rec, start, B, d, gU, gV, loss);
   if (rc != MFCD_OK) return rc;
   MFCD_REQUIRE(n_hot >= 0, "mfcd_triplet_fwd_bwd_hot: n_hot < 0");
-  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot,
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot, 0,
                                as_stream(stream));
+}
+
+extern "C" int mfcd_triplet_fwd_bwd_ex(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                                       int64_t start, int64_t B, int32_t d, float inv_batch, float* gU, float* gV,
+                                       float* loss, const int8_t* item_slot, const int32_t* hot_items,
+                                       int32_t n_hot, int32_t flags, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd_ex", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(n_hot >= 0, "mfcd_triplet_fwd_bwd_ex: n_hot < 0");
+  return launch_fwd_bwd_atomic(U, V, rec, perm, start, B, d, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot,
+                               flags, as_stream(stream));
 }
 
 extern "C" int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes) {
@@ -663,7 +695,7 @@ extern "C" int mfcd_train_epoch(const mfcd_epoch_args* a) {
                               a->step_losses + k, a->workspace, a->workspace_bytes, st);
     else
       rc = launch_fwd_bwd_atomic(U, V, a->rec, a->perm, start, B, a->d, inv_b, gU, gV, a->step_losses + k,
-                                 a->item_slot, a->hot_items, a->n_hot, st);
+                                 a->item_slot, a->hot_items, a->n_hot, a->flags, st);
     if (rc != MFCD_OK) return rc;
     const int64_t step = a->step0 + k + 1;
     if (a->optimizer == MFCD_OPT_ADAM)

@@ -112,10 +112,11 @@ class CudaEngine:
         else:
             hot = self.store.hot_items(fs.m, fs.d, b_local) if self.use_hot else None
             slot, items, n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
-            check(lib.mfcd_triplet_fwd_bwd_hot(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec),
-                                               ptr(self.perm), start, b_local, fs.d, inv, ptr(fs.grads),
-                                               ptr(fs.grads[nU:]), ptr(loss_slot), slot, items, n_hot,
-                                               current_stream()), "mfcd_triplet_fwd_bwd_hot")
+            check(lib.mfcd_triplet_fwd_bwd_ex(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec),
+                                              ptr(self.perm), start, b_local, fs.d, inv, ptr(fs.grads),
+                                              ptr(fs.grads[nU:]), ptr(loss_slot), slot, items, n_hot,
+                                              self.store.k1_flags(b_local, self.perm), current_stream()),
+                  "mfcd_triplet_fwd_bwd_ex")
 
     def update(self, a, b, step):
         fs, s = self.fs, self.spec

@@ -141,6 +141,55 @@ class TripletStore:
             check(lib.mfcd_unpack_triplets8(ptr(packed), N, ptr(rec), current_stream()), "mfcd_unpack_triplets8")
         return cls(rec)
 
+    def pack_wire(self, start, B):
+        """Records [start, start+B) (one user-grouped batch, hard labels, items < 65536) -> uint32 CUDA tensor in
+        the run-length wire format, trimmed to the words that have to travel (mfcd_pack_wire)."""
+        fixed, cap, wsb = C.c_int64(0), C.c_int64(0), C.c_size_t(0)
+        check(lib.mfcd_wire_layout(B, C.byref(fixed), C.byref(cap), C.byref(wsb)), "mfcd_wire_layout")
+        dev = self.device
+        with torch.cuda.device(dev):
+            wire = torch.empty(cap.value, dtype=torch.int32, device=dev)
+            ws = torch.empty(max(wsb.value, 1), dtype=torch.uint8, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            check(lib.mfcd_pack_wire(ptr(self.rec[start:start + B]), B, ptr(wire), cap.value, ptr(bad), ptr(ws),
+                                     wsb.value, current_stream()), "mfcd_pack_wire")
+            if int(bad.item()):
+                raise _lib.MfcdError("pack_wire: soft labels or item ids >= 65536 do not fit the run-length wire format")
+            n_runs = int(wire[0].item())
+        return wire[: fixed.value + n_runs]
+
+    @classmethod
+    def from_wire(cls, wire: torch.Tensor, B, out_rec: torch.Tensor = None):
+        """run-length wire words (CUDA int32/uint32) -> records; `out_rec` reuses an existing (B, 4) int32 buffer."""
+        rec = torch.empty((B, 4), dtype=torch.int32, device=wire.device) if out_rec is None else out_rec
+        with torch.cuda.device(wire.device):
+            check(lib.mfcd_unpack_wire(ptr(wire), B, ptr(rec), current_stream()), "mfcd_unpack_wire")
+        return cls(rec)
+
+    def group_by_user(self, batch_size):
+        """Reorder the records in place so that inside every batch of `batch_size` consecutive records one
+        user's triplets are adjacent (mfcd_group_by_user).  Batch membership is unchanged; K1 then reads
+        U[u] and reduces its gradient once per run (`flags` = FLAG_USER_GROUPED).  Only meaningful for
+        loaders that walk the store in order (no epoch permutation)."""
+        N = len(self)
+        batch_size = int(batch_size)
+        if N == 0 or getattr(self, "grouped_batch", None) == batch_size:
+            return self
+        need = C.c_size_t(0)
+        check(lib.mfcd_group_by_user_workspace(N, batch_size, C.byref(need)), "mfcd_group_by_user_workspace")
+        with torch.cuda.device(self.device):
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            check(lib.mfcd_group_by_user(ptr(self.rec), N, batch_size, ptr(ws), need.value, current_stream()),
+                  "mfcd_group_by_user")
+        self.grouped_batch = batch_size
+        self.__dict__.pop("_hot_cache", None)
+        return self
+
+    def k1_flags(self, batch_size, perm=None):
+        """flags for the atomic-mode K1 on batches of `batch_size` walked in store order"""
+        grouped = perm is None and getattr(self, "grouped_batch", None) == int(batch_size)
+        return _lib.FLAG_USER_GROUPED if grouped else 0
+
     def hot_items(self, n_items, d, batch_size, min_hits_per_batch=2048, sample=1 << 24):
         """Item rows that would each receive >= min_hits_per_batch gradient updates per batch
         (popularity-biased sampling): candidates for K1's shared-memory privatisation.

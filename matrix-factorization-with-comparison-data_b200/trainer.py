@@ -203,7 +203,8 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     a = _lib.EpochArgs()
     a.params, a.grads, a.state1, a.state2 = ptr(fs.params), ptr(fs.grads), ptr(fs.state1), ptr(fs.state2)
     a.n_users, a.n_items, a.d = fs.n, fs.m, fs.d
-    a.optimizer, a.mode, a.reserved = spec.kind, mode, 0
+    a.optimizer, a.mode = spec.kind, mode
+    a.flags = store.k1_flags(batch_size, perm) if mode == MODE_ATOMIC else 0
     a.rec, a.perm = ptr(store.rec), ptr(perm)
     a.n_samples, a.batch_size = N, batch_size
     a.lr, a.beta1, a.beta2, a.eps = spec.lr, spec.beta1, spec.beta2, spec.eps

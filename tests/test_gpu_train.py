@@ -124,6 +124,94 @@ def test_hot_row_privatisation_matches_oracle(G, d):
     assert rc == -1
 
 
+def test_group_by_user_keeps_batches_and_brings_users_together(G):
+    """mfcd_group_by_user: every batch holds the same records as before, one user's triplets are adjacent,
+    and a user's triplets keep their order (stable); ragged last batch included."""
+    rng = np.random.default_rng(3)
+    N, B, n, m = 10_000, 768, 97, 50
+    u, i, j = rng.integers(0, n, N), rng.integers(0, m, N), rng.integers(0, m, N)
+    z = rng.integers(0, 2, N).astype(np.float64)
+    store = G.store_from(u, i, j, z)
+    before = store.rec.cpu().numpy().copy()
+    store.group_by_user(B)
+    after = store.rec.cpu().numpy()
+    assert store.k1_flags(B) == 1 and store.k1_flags(B + 1) == 0 and store.k1_flags(B, perm=object()) == 0
+    for s0 in range(0, N, B):
+        a, b = before[s0:s0 + B], after[s0:s0 + B]
+        order = np.argsort(a[:, 0], kind="stable")
+        assert np.array_equal(a[order], b)              # same records, sorted by user, stable
+
+
+@pytest.mark.parametrize("N,n", [(1, 5), (31, 3), (32, 40), (8191, 70), (8192, 1), (8193, 5000), (100_003, 999)])
+def test_run_length_wire_format_round_trip(G, N, n):
+    """pack_wire -> (host) -> from_wire gives back the grouped batch bit for bit; sizes around word / block edges."""
+    rng = np.random.default_rng(N)
+    u, i, j = rng.integers(0, n, N), rng.integers(0, 65536, N), rng.integers(0, 65536, N)
+    z = rng.integers(0, 2, N).astype(np.float64)
+    store = G.store_from(u, i, j, z).group_by_user(N)
+    wire = store.pack_wire(0, N)
+    runs = len(np.unique(u))
+    assert int(wire[0].item()) == runs and int(wire[1].item()) == N
+    assert wire.numel() == 4 + (N + 31) // 32 * 3 + N + runs
+    back = G.TripletStore.from_wire(wire.cpu().to(G.DEV), N)          # through host memory, like the bench
+    assert torch.equal(back.rec, store.rec)
+    # soft labels / wide item ids are refused, not mangled
+    bad = G.store_from([0], [70000], [1], [1.0])
+    with pytest.raises(Exception):
+        bad.pack_wire(0, 1)
+    soft = G.store_from([0], [2], [1], [0.5])
+    with pytest.raises(Exception):
+        soft.pack_wire(0, 1)
+
+
+@pytest.mark.parametrize("d,hot", [(64, False), (64, True), (32, True), (128, True), (256, False), (16, False)])
+def test_user_grouped_kernel_matches_oracle(G, d, hot):
+    """K1 with MFCD_FLAG_USER_GROUPED (one U read / one gU reduction per run of equal users, hottest item
+    rows in registers) == oracle, on grouped batches, on a ragged tail, and on UNGROUPED data (the flag is
+    only a hint)."""
+    import ctypes as C
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(100 + d + hot)
+    n, m, B = 150, 300, 20011
+    U, V, u, i, j, z = _random_problem(rng, n, m, d, B, hot=hot)
+    keep = i != j
+    u, i, j, z = u[keep], i[keep], j[keep], z[keep]
+    B = len(u)
+    lo, gUo, gVo = O.loss_and_grads(U, V, u, i, j, z.astype(np.float32))
+    Ud, Vd = G.dev_f32(U), G.dev_f32(V)
+    for grouped in (True, False):
+        store = G.store_from(u, i, j, z)
+        if grouped:
+            store.group_by_user(B)
+        hi = store.hot_items(m, d, B, min_hits_per_batch=200) if hot else None
+        slot, items, nh = (ptr(hi[0]), ptr(hi[1]), hi[1].numel()) if hi else (None, None, 0)
+        gU = torch.zeros_like(Ud); gV = torch.zeros_like(Vd); loss = torch.zeros(1, device=G.DEV)
+        check(lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(store.rec), None, 0, B, d, 1.0 / B, ptr(gU), ptr(gV),
+                                          ptr(loss), slot, items, nh, 1, current_stream()), "ex")
+        assert abs(loss.item() - lo) < 2e-5 * abs(lo), (grouped, loss.item(), lo)
+        assert G.rel(gU.cpu().numpy(), gUo) < 2e-5 and G.rel(gV.cpu().numpy(), gVo) < 2e-5, grouped
+        if grouped and m <= 65536:
+            # the same batch in the run-length wire format, decoded by K1 itself (MFCD_FLAG_WIRE_RLE)
+            wire = store.pack_wire(0, B)
+            gU2 = torch.zeros_like(Ud); gV2 = torch.zeros_like(Vd); loss2 = torch.zeros(1, device=G.DEV)
+            check(lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(wire), None, 0, B, d, 1.0 / B, ptr(gU2), ptr(gV2),
+                                              ptr(loss2), slot, items, nh, 1 | 2, current_stream()), "ex-wire")
+            assert abs(loss2.item() - lo) < 2e-5 * abs(lo)
+            assert G.rel(gU2.cpu().numpy(), gUo) < 2e-5 and G.rel(gV2.cpu().numpy(), gVo) < 2e-5
+            rc = lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(wire), None, 5, B - 5, d, 1.0 / B, ptr(gU2), ptr(gV2),
+                                             ptr(loss2), slot, items, nh, 1 | 2, current_stream())
+            assert rc == -1                                  # a wire batch is read whole
+    # two half batches (second one starts mid-run and ends on a partial tile) accumulate to the full batch
+    store = G.store_from(u, i, j, z).group_by_user(B)
+    gU = torch.zeros_like(Ud); gV = torch.zeros_like(Vd); loss = torch.zeros(1, device=G.DEV)
+    h = B // 2 + 5
+    for s0, cnt in ((0, h), (h, B - h)):
+        check(lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(store.rec), None, s0, cnt, d, 1.0 / B, ptr(gU), ptr(gV),
+                                          ptr(loss), None, None, 0, 1, current_stream()), "ex")
+    assert abs(loss.item() - lo) < 2e-5 * abs(lo)
+    assert G.rel(gU.cpu().numpy(), gUo) < 2e-5 and G.rel(gV.cpu().numpy(), gVo) < 2e-5
+
+
 def test_deterministic_mode_is_bit_reproducible(G):
     rng = np.random.default_rng(7)
     U, V, u, i, j, z = _random_problem(rng, 500, 64, 64, 20000, hot=True)
