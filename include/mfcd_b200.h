@@ -215,6 +215,12 @@ typedef struct mfcd_epoch_args {
   int32_t reserved2;
 } mfcd_epoch_args;
 int mfcd_train_epoch(const mfcd_epoch_args* args);
+/* Workspace mfcd_train_epoch wants for these arguments (0 = none).  In the reference's own regime --
+ * deterministic mode, batch <= 256, Adam, tables of up to ~600k elements -- the whole epoch runs as ONE
+ * persistent cooperative kernel (epoch_small.cu: per-CTA ownership of table slices, parameters and Adam
+ * moments in registers, ping-pong parameter buffers, one grid barrier per step) instead of two launches
+ * per step; the workspace holds the second parameter buffer.  Without it the per-step launches are used. */
+int mfcd_train_epoch_workspace(const mfcd_epoch_args* args, size_t* bytes);
 
 /* ---- K4: evaluation ----------------------------------------------------------
  * evaluate_model (structure.py:896-921) and the validation pass of train_model

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mfcd_dp_fused_adam": [C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32, F32, F32, F32, F32,
                            I64, P],
     "mfcd_train_epoch": [C.POINTER(EpochArgs)],
+    "mfcd_train_epoch_workspace": [C.POINTER(EpochArgs), C.POINTER(SZ)],
     "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P],
     "mfcd_ground_truth_eval": [C.POINTER(XView), P, I64, I64, P, P, P],
     "mfcd_triplet_scores": [P, P, P, P, P, I64, I32, P, P],

@@ -7,20 +7,6 @@
 
 namespace mfcd {
 
-struct AdamScalars {
-  float lr_over_bc1;   // lr / (1 - beta1^t)
-  float bc2_sqrt;      // sqrt(1 - beta2^t)
-  float one_minus_b1, b2, one_minus_b2, eps, wd;
-};
-
-__device__ __forceinline__ void adam_elem(float& p, float& g, float& m, float& v, const AdamScalars& s) {
-  float gg = (s.wd != 0.f) ? fmaf(s.wd, p, g) : g;          // grad.add(param, alpha=wd)
-  m = fmaf(gg - m, s.one_minus_b1, m);                      // exp_avg.lerp_(grad, 1-beta1)
-  v = fmaf(s.one_minus_b2 * gg, gg, v * s.b2);              // mul_(beta2).addcmul_(g, g, 1-beta2)
-  float denom = sqrtf(v) / s.bc2_sqrt + s.eps;              // (sqrt(v)/bc2_sqrt).add_(eps)
-  p = fmaf(-s.lr_over_bc1, m / denom, p);                   // addcdiv_(m, denom, value=-step_size)
-}
-
 template <bool ZERO>
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ v, int64_t numel, AdamScalars s) {
@@ -73,17 +59,7 @@ int launch_adam(float* p, float* g, float* m, float* v, int64_t numel, float lr,
   MFCD_REQUIRE(p && g && m && v, "adam: NULL pointer");
   MFCD_REQUIRE(step >= 1, "adam: step must be >= 1 (1-based)");
   MFCD_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam: buffers must be 16-byte aligned");
-  AdamScalars s;
-  // bias corrections in double like the python floats of torch's _single_tensor_adam
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  s.lr_over_bc1 = (float)((double)lr / bc1);
-  s.bc2_sqrt = (float)sqrt(bc2);
-  s.one_minus_b1 = (float)(1.0 - (double)beta1);
-  s.b2 = beta2;
-  s.one_minus_b2 = (float)(1.0 - (double)beta2);
-  s.eps = eps;
-  s.wd = wd;
+  const AdamScalars s = adam_scalars(lr, beta1, beta2, eps, wd, step);
   const int grid = grid_for((numel + 3) / 4, 256, 8);
   if (zero_grad) k_adam<true><<<grid, 256, 0, st>>>(p, g, m, v, numel, s);
   else k_adam<false><<<grid, 256, 0, st>>>(p, g, m, v, numel, s);

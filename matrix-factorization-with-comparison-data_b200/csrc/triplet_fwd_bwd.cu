@@ -684,6 +684,10 @@ extern "C" int mfcd_train_epoch(const mfcd_epoch_args* a) {
   float* gV = a->grads + a->n_users * a->d;
   const int64_t n_steps = (a->n_samples + a->batch_size - 1) / a->batch_size;
   if (n_steps == 0) return MFCD_OK;
+  {   // reference regime (small batch, deterministic, Adam, small tables): one persistent kernel for the epoch
+    const int rc = launch_epoch_small(a, st);
+    if (rc != MFCD_ERR_UNSUPPORTED) return rc;
+  }
   MFCD_CUDA(cudaMemsetAsync(a->step_losses, 0, sizeof(float) * n_steps, st));
   for (int64_t k = 0; k < n_steps; ++k) {
     const int64_t start = k * a->batch_size;

@@ -196,10 +196,6 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     losses = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=dev)
     if n_steps == 0:
         return losses[:0]
-    ws_bytes = C.c_size_t(0)
-    if mode == MODE_DETERMINISTIC:
-        check(lib.mfcd_det_workspace_bytes(min(batch_size, N), fs.d, C.byref(ws_bytes)), "mfcd_det_workspace_bytes")
-    ws = fs.ensure_workspace(ws_bytes.value)
     a = _lib.EpochArgs()
     a.params, a.grads, a.state1, a.state2 = ptr(fs.params), ptr(fs.grads), ptr(fs.state1), ptr(fs.state2)
     a.n_users, a.n_items, a.d = fs.n, fs.m, fs.d
@@ -211,6 +207,9 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     a.weight_decay, a.momentum = spec.weight_decay, spec.momentum
     a.step0 = fs.step
     a.step_losses = ptr(losses)
+    ws_bytes = C.c_size_t(0)
+    check(lib.mfcd_train_epoch_workspace(C.byref(a), C.byref(ws_bytes)), "mfcd_train_epoch_workspace")
+    ws = fs.ensure_workspace(ws_bytes.value)
     a.workspace, a.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
     hot = store.hot_items(fs.m, fs.d, batch_size) if mode == MODE_ATOMIC else None
     a.item_slot, a.hot_items, a.n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)

@@ -316,6 +316,43 @@ def test_epoch_runner_matches_reference_steps(G, name, mode):
     assert G.rel(model.V.detach().cpu().numpy(), g["V1"]) < 1e-5
 
 
+@pytest.mark.parametrize("n,m,d,steps,batch,lr,wd", [
+    (1500, 700, 10, 150, 64, 1e-2, 1e-4), (1000, 1000, 2, 120, 64, 1e-2, 1e-4), (3000, 2000, 32, 60, 64, 1e-2, 1e-4),
+    (400, 300, 64, 41, 200, 1e-2, 1e-4),
+    # rows that are hardly ever touched only follow the weight decay; at lr = 1e-2 their Adam quotient
+    # m / (sqrt(v) + eps) of tiny numbers drifts 6e-6 from numpy's in 80 steps on BOTH GPU paths (identical
+    # values, MFCD_EPOCH_KERNEL=0/1), so this case runs at the reference's own lr / wd
+    (5000, 4000, 8, 80, 7, 1e-3, 1e-5)])
+def test_persistent_epoch_kernel_many_ctas_vs_oracle(G, n, m, d, steps, batch, lr, wd):
+    """The one-kernel epoch (tables split over several CTAs, ping-pong parameters, grid barrier per step):
+    per-step loss, U, V and a SECOND epoch (odd/even step counts, Adam state carried over, permuted order)
+    against the numpy oracle, 1e-5 relative.  Ragged last batch included."""
+    from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec, run_epoch
+    rng = np.random.default_rng(n + d)
+    N = steps * batch - 3
+    U0 = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    V0 = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    u, i, j = rng.integers(0, n, N), rng.integers(0, m, N), rng.integers(0, m, N)
+    u[:40] = 3; i[:20] = 5; j[20:40] = 5                       # repeated rows inside one batch, i and j sides
+    z = rng.integers(0, 2, N).astype(np.float64)
+    perm2 = rng.permutation(N)
+    model = MatrixFactorization(n, m, d)
+    with torch.no_grad():
+        model.U.copy_(torch.from_numpy(U0)); model.V.copy_(torch.from_numpy(V0))
+    fs = model.flat_state(G.DEV)
+    spec = OptimizerSpec.adam(lr=lr, weight_decay=wd)
+    store = G.store_from(u, i, j, z)
+    l1 = run_epoch(fs, store, None, batch, spec, 1).cpu().numpy()
+    l2 = run_epoch(fs, store, torch.from_numpy(perm2).to(G.DEV, torch.int32), batch, spec, 1).cpu().numpy()
+    Uo, Vo = U0.copy(), V0.copy()
+    lo1, st = O.train_steps(Uo, Vo, O.split_batches(u, i, j, z, batch), lr, wd)
+    lo2, st = O.train_steps(Uo, Vo, O.split_batches(u, i, j, z, batch, order=perm2), lr, wd, state=st)
+    assert G.rel(l1, lo1) < 1e-5 and G.rel(l2, lo2) < 1e-5
+    assert G.rel(model.U.detach().cpu().numpy(), Uo) < 1e-5 and G.rel(model.V.detach().cpu().numpy(), Vo) < 1e-5
+    assert not fs.grads.any().item()                            # the gradient buffer is never touched
+    assert fs.step == 2 * steps
+
+
 @pytest.mark.parametrize("name", TRAIN_FIXTURES)
 def test_step_snapshots(G, name):
     from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec, run_epoch

@@ -1,0 +1,7 @@
+set -u
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_train.py tests/test_gpu_dropin.py -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_small.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/pytest_small.log
+timeout 120 python tools/small_step_probe.py 1000 1000 10 9375 | tail -1
+timeout 120 python tools/small_step_probe.py 100 100 2 2000 | tail -1
+timeout 120 python tools/small_step_probe.py 10000 5000 32 2000 | tail -1
+timeout 120 python tools/small_step_probe.py 1000 1000 64 2000 | tail -1
