@@ -13,7 +13,8 @@
 //   * ONE thread issues tcgen05.mma (kind::tf32, M = 128, N = 64, K = 8 per instruction), three MMAs per
 //     K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's sgemm), accumulating in TMEM
 //     (2 stages x 64 columns);
-//   * eight epilogue warps (TMEM lane quarter = warp id % 4, column half = warp id / 4) read the
+//   * sixteen epilogue warps (TMEM lane quarter = warp id % 4, 16-column quarter = warp id / 4; eight warps
+//     with 32 columns each left the pipeline waiting on the epilogue: 2.5 us per tile against 0.4 for the MMAs) read the
 //     accumulators with tcgen05.ld, the X tile from swizzled shared memory, and fold both into per-row
 //     fp64 sums.
 // mbarriers connect the roles; every wait is bounded, so a pipeline bug raises an error flag and lets
@@ -29,7 +30,7 @@ constexpr int TN = 64;                  // tile cols  (UMMA N, TMEM columns per 
 constexpr int KMAX = 64;                // largest K handled (2 swizzle slabs)
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
 constexpr int NSTAGE = 2;
-constexpr int EPI_WARPS = 8;            // warp w: TMEM lane quarter w % 4, column half w / 4
+constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 16-column quarter of the tile w / 4
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
@@ -143,12 +144,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- pre-pass: hi/lo split of a table into K-padded staging arrays + its row-wise dot with `other_mean` ----
-__global__ void __launch_bounds__(256)
-k_split_table(const float* __restrict__ T, int64_t rows, int d, int kpad, const float* __restrict__ other_mean,
-              float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ dots) {
+// ---- pre-pass (ONE launch): hi/lo split of both tables into K-padded staging arrays, their row-wise dots with
+// the other table's column mean (a_r = <U_r, vbar>, b_c = <ubar, V_c>), and the zeroing of the outputs ----
+__device__ __forceinline__ void split_table(const float* __restrict__ T, int64_t rows, int d, int kpad,
+                                            const float* __restrict__ other_mean, float* __restrict__ hi,
+                                            float* __restrict__ lo, float* __restrict__ dots, int64_t dots_len,
+                                            int64_t tid, int64_t nth) {
   const int64_t total = rows * kpad;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t idx = tid; idx < total; idx += nth) {
     const int64_t r = idx / kpad;
     const int k = (int)(idx - r * kpad);
     const float v = k < d ? __ldg(T + r * d + k) : 0.f;
@@ -156,11 +159,25 @@ k_split_table(const float* __restrict__ T, int64_t rows, int d, int kpad, const 
     hi[idx] = h;
     lo[idx] = v - h;
   }
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t r = tid; r < dots_len; r += nth) {
     float acc = 0.f;
-    for (int k = 0; k < d; ++k) acc = fmaf(__ldg(T + r * d + k), __ldg(other_mean + k), acc);
-    dots[r] = acc;
+    if (r < rows)
+      for (int k = 0; k < d; ++k) acc = fmaf(__ldg(T + r * d + k), __ldg(other_mean + k), acc);
+    dots[r] = acc;                                   // padding entries (r >= rows) are zero
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_tc_prepass(const float* __restrict__ U, const float* __restrict__ V, int64_t n, int64_t m, int d, int kpad,
+             const float* __restrict__ ubar, const float* __restrict__ vbar, float* __restrict__ u_hi,
+             float* __restrict__ u_lo, float* __restrict__ v_hi, float* __restrict__ v_lo, float* __restrict__ avec,
+             float* __restrict__ bvec, int64_t bvec_len, double* __restrict__ row_stats, int* __restrict__ error_flag) {
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  split_table(U, n, d, kpad, vbar, u_hi, u_lo, avec, n, tid, nth);
+  split_table(V, m, d, kpad, ubar, v_hi, v_lo, bvec, bvec_len, tid, nth);
+  for (int64_t k = tid; k < 8 * n; k += nth) row_stats[k] = 0.0;
+  if (tid == 0) *error_flag = 0;
 }
 
 struct Maps {
@@ -209,18 +226,25 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
   uint32_t use = 0;       // tiles processed so far by this CTA: B/TMEM stage = use % 2, X slot = use % ring
   uint32_t item = 0;      // work items processed so far: phase of a_full
 
-  for (int64_t work = blockIdx.x; work < row_tiles * col_splits; work += gridDim.x, ++item) {
-    const int64_t rt = work / col_splits;
-    const int split = (int)(work % col_splits);
+  // Balanced persistent schedule: the row-major tile sequence is cut into gridDim.x equal ranges (+-1 tile);
+  // a CTA walks its range one row block at a time (row blocks x fixed column splits left 24 of 148 CTAs with
+  // a third work item while the others idled: 72 % wave efficiency).
+  (void)col_splits;
+  const int64_t total_tiles = row_tiles * col_tiles;
+  const int64_t t_begin = total_tiles * blockIdx.x / gridDim.x;
+  const int64_t t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+  for (int64_t tpos = t_begin; tpos < t_end; ++item) {
+    const int64_t rt = tpos / col_tiles;
     const int row0 = (int)(rt * TM);
-    const int64_t ct_begin = col_tiles * split / col_splits;
-    const int64_t ct_end = col_tiles * (split + 1) / col_splits;
+    const int64_t ct_begin = tpos - rt * col_tiles;
+    const int64_t ct_end = (t_end - rt * col_tiles) < col_tiles ? (t_end - rt * col_tiles) : col_tiles;
     const int ntiles = (int)(ct_end - ct_begin);
+    tpos += ntiles;
 
     if (warp < EPI_WARPS) {
-      // ===== epilogue: thread owns tile row t (TMEM lane t) and one 32-column half of the tile =====
+      // ===== epilogue: thread owns tile row t (TMEM lane t) and one 16-column quarter of the tile =====
       const int t = (warp & 3) * 32 + lane;
-      const int half = warp >> 2;
+      const int quarter = warp >> 2;                              // columns quarter*16 .. +15 of the tile
       const int64_t gr = (int64_t)row0 + t;
       const float a_row = gr < n ? __ldg(avec + gr) : 0.f;
       const int sw = t & 7;
@@ -232,24 +256,36 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
         if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
         if (!mbar_wait(&tl.mma_done[st], ph, err)) break;       // accumulators complete
         tc_fence_after();
-        const float* xbox = reinterpret_cast<const float*>(x_base + slot * XSLOT_BYTES + half * X_BOX_BYTES) + t * SLAB_K;
-        const float* bcol = &tl.b_col[slot][half * 32];
+        // X box (32 columns) that holds this quarter, and the quarter's first 16-byte chunk inside the box row
+        const float* xbox = reinterpret_cast<const float*>(x_base + slot * XSLOT_BYTES + (quarter >> 1) * X_BOX_BYTES) + t * SLAB_K;
+        const int chunk0 = (quarter & 1) * 4;
+        const float* bcol = &tl.b_col[slot][quarter * 16];
         float sx = 0.f, sxx = 0.f, swm = 0.f, sww = 0.f, sxw = 0.f, see = 0.f;
-        const int valid = (int)((m - (col0 + half * 32)) < 32 ? (m - (col0 + half * 32)) : 32);   // columns of this half inside X
+        const int64_t left = m - (col0 + quarter * 16);
+        const int valid = (int)(left < 16 ? (left < 0 ? 0 : left) : 16);      // columns of this quarter inside X
+        float w[16];
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + st * TN + quarter * 16, w);
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          float w[16];
-          tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + st * TN + half * 32 + c0, w);
+        for (int q = 0; q < 16; q += 4) {
+          const int chunk = chunk0 + (q >> 2);                     // 16-byte chunk inside the box row, un-swizzle
+          const float4 xv = *reinterpret_cast<const float4*>(xbox + ((chunk ^ sw) << 2));
+          const float4 bv = *reinterpret_cast<const float4*>(bcol + q);
+          const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+          const float bs4[4] = {bv.x, bv.y, bv.z, bv.w};
+          if (valid >= 16) {                                       // interior tile: no per-element bounds checks
 #pragma unroll
-          for (int q = 0; q < 16; q += 4) {
-            const int chunk = (c0 + q) >> 2;                       // 16-byte chunk inside the row, un-swizzle
-            const float4 xv = *reinterpret_cast<const float4*>(xbox + ((chunk ^ sw) << 2));
-            const float4 bv = *reinterpret_cast<const float4*>(bcol + c0 + q);
-            const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float bs4[4] = {bv.x, bv.y, bv.z, bv.w};
-            if (valid >= 32) {                                     // interior tile: no per-element bounds checks
+            for (int e = 0; e < 4; ++e) {
+              const float x = xs4[e];
+              const float wa = w[q + e] - a_row;
+              const float ee = (w[q + e] - bs4[e]) - s * x;
+              sx += x; sxx = fmaf(x, x, sxx);
+              swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
+              see = fmaf(ee, ee, see);
+            }
+          } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 4; ++e) {
+              if (q + e < valid) {
                 const float x = xs4[e];
                 const float wa = w[q + e] - a_row;
                 const float ee = (w[q + e] - bs4[e]) - s * x;
@@ -257,32 +293,20 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
                 swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
                 see = fmaf(ee, ee, see);
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (c0 + q + e < valid) {
-                  const float x = xs4[e];
-                  const float wa = w[q + e] - a_row;
-                  const float ee = (w[q + e] - bs4[e]) - s * x;
-                  sx += x; sxx = fmaf(x, x, sxx);
-                  swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
-                  see = fmaf(ee, ee, see);
-                }
-              }
             }
           }
         }
         tc_fence_before();
         mbar_arrive(&tl.x_free[slot]);
         mbar_arrive(&tl.tmem_free[st]);
-        // 32-element fp32 partials, fp64 across tiles
+        // 16-element fp32 partials, fp64 across tiles
         acc[0] += (double)sx; acc[1] += (double)sxx; acc[2] += (double)swm;
         acc[3] += (double)sww; acc[4] += (double)sxw; acc[5] += (double)see;
       }
       if (gr < n) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) atomicAdd(row_stats + gr * 8 + q, acc[q]);
-        if (split == 0 && half == 0) row_stats[gr * 8 + 6] = (double)a_row;
+        if (ct_begin == 0 && quarter == 0) row_stats[gr * 8 + 6] = (double)a_row;
       }
     } else if (warp == PRODUCER_WARP) {
       // ================= TMA producer (one elected thread) =================
@@ -459,12 +483,9 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   if ((rc = tc::make_map(&maps.v_hi, v_hi, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
   if ((rc = tc::make_map(&maps.v_lo, v_lo, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
 
-  MFCD_CUDA(cudaMemsetAsync(row_stats, 0, sizeof(double) * 8 * n, st));
-  MFCD_CUDA(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), st));
-  tc::k_split_table<<<grid_for(n * kpad, 256, 8), 256, 0, st>>>(U, n, d, kpad, vbar, u_hi, u_lo, avec);
-  MFCD_CHECK_LAUNCH();
-  MFCD_CUDA(cudaMemsetAsync(bvec, 0, sizeof(float) * ((m + tc::TN - 1) / tc::TN * tc::TN), st));
-  tc::k_split_table<<<grid_for(m * kpad, 256, 8), 256, 0, st>>>(V, m, d, kpad, ubar, v_hi, v_lo, bvec);
+  const int64_t bvec_len = (m + tc::TN - 1) / tc::TN * tc::TN;
+  tc::k_tc_prepass<<<grid_for((n + m) * kpad, 256, 8), 256, 0, st>>>(U, V, n, m, d, kpad, ubar, vbar, u_hi, u_lo, v_hi,
+                                                                     v_lo, avec, bvec, bvec_len, row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
 
   const int64_t row_tiles = (n + tc::TM - 1) / tc::TM;
