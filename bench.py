@@ -398,9 +398,10 @@ def main():
         best = "wire_rle" if "wire_rle" in e2e_formats else ("wire8" if "wire8" in e2e_formats else list(e2e_formats)[0])
         e2e = dict(e2e_formats[best])
         e2e["format"] = best
-        e2e["how"] = ("pinned host batches in the '%s' staging format -> cudaMemcpyAsync + unpack kernel (double-buffered "
-                      "on a copy stream) -> K1 -> exchange -> update -> loss.item() each step; wall clock, max over "
-                      "ranks. records16 = the 16-byte HBM records; wire8 = 8-byte hard-label records; wire_rle = "
+        e2e["how"] = ("pinned host batches in the '%s' staging format -> cudaMemcpyAsync (double-buffered on a copy "
+                      "stream; wire8 adds an unpack kernel) -> K1 -> exchange -> update -> the step's loss copied back "
+                      "and read by the host every step (the read of step k overlaps the launch of step k+1); wall "
+                      "clock, max over ranks. records16 = the 16-byte HBM records; wire8 = 8-byte hard-label records; wire_rle = "
                       "run-length format of a user-grouped batch, decoded by K1 itself (include/mfcd_b200.h: mfcd_pack_wire, "
                       "MFCD_FLAG_WIRE_RLE)" % best)
         e2e["other_formats"] = {f: {"value": v["value"], "h2d_bytes_per_step": v["h2d_bytes_per_step"]}
@@ -450,9 +451,11 @@ def main():
                        "batch_layout": ("grouped by user inside each batch" if k1_flags else "sampler order"),
                        "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB) are L2-resident "
                                     "by design of the algorithm"},
-            "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_lean (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_triplet": bytes_per_triplet, "k1_ms": k1_ms,
+                         "limiter": "ncu (profiles/r01c_ncu_k1_lean_full_summary.json): issue slots 66 %, LSU data pipe "
+                                    "60 %, L2 12 %, DRAM 4 % -- the 38 MB tables and their gradients are served by L1/L2",
                          "k1_share_of_step": k1_ms / (ms / K),
                          "note": "achieved = (16 + 24 d) algorithmic bytes x triplets / K1 time (SURVEY 8d). The "
                                  "embedding tables and their gradients (2 x 38.4 MB at config 4) stay L2-resident, so "

@@ -155,6 +155,14 @@ def test_run_length_wire_format_round_trip(G, N, n):
     assert wire.numel() == 4 + (N + 31) // 32 * 3 + N + runs
     back = G.TripletStore.from_wire(wire.cpu().to(G.DEV), N)          # through host memory, like the bench
     assert torch.equal(back.rec, store.rec)
+    # the device packer against the numpy restatement of the layout, bit for bit, and the device unpacker on
+    # words the oracle packed
+    from oracle import wire_oracle as W
+    gu, gi, gj, gz = [c.cpu().numpy() for c in store.columns()]
+    ow = W.pack_wire(gu, gi, gj, gz)
+    assert np.array_equal(wire.cpu().numpy().view(np.uint32), ow)
+    back2 = G.TripletStore.from_wire(torch.from_numpy(ow.view(np.int32)).to(G.DEV), N)
+    assert torch.equal(back2.rec, store.rec)
     # soft labels / wide item ids are refused, not mangled
     bad = G.store_from([0], [70000], [1], [1.0])
     with pytest.raises(Exception):
