@@ -74,3 +74,32 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setenv("MFCD_B200_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.MfcdError):
         _lib._load()
+
+
+def _epoch_ws(n, m, d, batch, N, mode=1, opt=0):
+    from mfcd_b200 import _lib
+    a = _lib.EpochArgs()
+    a.n_users, a.n_items, a.d = n, m, d
+    a.mode, a.optimizer = mode, opt
+    a.batch_size, a.n_samples = batch, N
+    a.beta1, a.beta2 = 0.9, 0.999
+    out = C.c_size_t(0)
+    assert _lib.lib.mfcd_train_epoch_workspace(C.byref(a), C.byref(out)) == 0
+    return out.value
+
+
+def test_epoch_workspace_says_when_the_persistent_kernel_applies():
+    """Host-side plan of mfcd_train_epoch (no GPU needed): the reference's regime -- deterministic, Adam, batch <= 256,
+    small tables -- asks for the second parameter buffer + the per-step bias table; everything else asks for
+    nothing (atomic mode, SGD, huge tables) or for the sort workspace of the large deterministic path."""
+    n, m, d, N = 1000, 1000, 10, 600_000
+    steps = (N + 63) // 64
+    need = _epoch_ws(n, m, d, 64, N)
+    assert 4 * (n + m) * d + 8 * steps <= need <= 4 * (n + m) * d + 8 * steps + 3 * 256
+    assert _epoch_ws(100, 100, 2, 64, 400) >= 4 * 400 + 8 * 7          # config 1: 7 steps per epoch
+    assert _epoch_ws(n, m, d, 64, N, mode=0) == 0                      # atomic mode: per-step launches
+    assert _epoch_ws(n, m, d, 64, N, opt=1) == 0                       # SGD: per-step launches
+    assert _epoch_ws(100_000, 50_000, 64, 64, 1000) == 0               # 9.6 M elements do not fit the register slices
+    big = _epoch_ws(n, m, d, 512, N)                                   # batch > 256: sort + segmented reduction
+    assert big > 0 and big != need
+    assert _epoch_ws(101, 100, 3, 64, 400) > 0                         # odd d: scalar rows, still eligible
