@@ -393,6 +393,8 @@ def main():
             return out
 
         formats = ["records16", "wire8"] + (["wire_rle"] if (k1_flags and m <= 65536 and mode == 0 and d % 4 == 0) else [])
+        if "wire_rle" in formats and total_steps * B * 16 > (4 << 30):
+            formats = ["wire_rle"]      # long runs: do not pin gigabytes of host memory for the comparison formats
         for fmt in (formats if args.e2e_format == "all" else [args.e2e_format]):
             e2e_formats[fmt] = run_format(fmt)
         best = "wire_rle" if "wire_rle" in e2e_formats else ("wire8" if "wire8" in e2e_formats else list(e2e_formats)[0])
