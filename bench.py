@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=1 << 22, help="triplets per GPU per step")
     ap.add_argument("--mode", default="atomic", choices=["atomic", "deterministic"])
-    ap.add_argument("--cpu-batch", type=int, default=65536)
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="triplets per step of the CPU legs; 0 = the GPU arm's batch when the host can afford it")
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = sized for ~15 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -127,6 +128,19 @@ class ClockSampler:
                 "reasons": reasons}
 
 
+def cpu_batch_for(TP, cfg, probs, want_batch, steps, budget_s, threads, floor=65536):
+    """Largest batch <= want_batch (halving, never below `floor`) at which `steps` reference steps fit `budget_s`
+    seconds on this host; -> (batch, seconds per step of the probe).  The reference's dense Adam costs the same per
+    step whatever the batch, so the GPU arm's own batch is the fair sample when the box can afford it."""
+    batch = want_batch
+    while True:
+        _, sps, _ = TP.time_train_steps(cfg["n"], cfg["m"], cfg["d"], batch, steps=1, warmup=1, item_probs=probs,
+                                        threads=threads)
+        if sps * steps <= budget_s or batch // 2 < floor:
+            return batch, sps
+        batch //= 2
+
+
 def reference_arm(args, cfg, rank):
     """--impl reference: the reference's CPU implementation of the step (oracle/torch_port.py: the same ATen
     ops, pinned bit-exact to the reference by the tests) on the box's host cores, all threads."""
@@ -139,7 +153,9 @@ def reference_arm(args, cfg, rank):
     probs = None
     if cfg["dist"] == "zipf":
         probs = 1.0 / torch.arange(1, cfg["m"] + 1, dtype=torch.float64) ** cfg["alpha"]
-    B = args.cpu_batch
+    # same batch as the GPU arm when steps + warm-up fit ~150 s of host time, else the largest halving that does
+    B = args.cpu_batch if args.cpu_batch > 0 else cpu_batch_for(TP, cfg, probs, args.batch, args.steps + args.warmup,
+                                                                150.0, threads)[0]
     tps, sps, used = TP.time_train_steps(cfg["n"], cfg["m"], cfg["d"], B, steps=args.steps, warmup=args.warmup,
                                          item_probs=probs)
     line = {
@@ -418,13 +434,17 @@ def main():
             probs = 1.0 / torch.arange(1, m + 1, dtype=torch.float64) ** cfg["alpha"]
         threads = os.cpu_count() or 1
         csteps = args.cpu_steps
+        if args.cpu_batch > 0:
+            cbatch = args.cpu_batch
+            _, sps, _ = TP.time_train_steps(n, m, d, cbatch, steps=1, warmup=1, item_probs=probs, threads=threads)
+        else:       # the GPU arm's batch if 3 steps of it fit ~20 s, else the largest halving that does
+            cbatch, sps = cpu_batch_for(TP, cfg, probs, B, 3, 20.0, threads)
         if csteps == 0:
-            _, sps, _ = TP.time_train_steps(n, m, d, args.cpu_batch, steps=2, warmup=1, item_probs=probs, threads=threads)
             csteps = max(3, min(200, int(15.0 / max(sps, 1e-3))))
-        tps, sps, used = TP.time_train_steps(n, m, d, args.cpu_batch, steps=csteps, warmup=1, item_probs=probs,
+        tps, sps, used = TP.time_train_steps(n, m, d, cbatch, steps=csteps, warmup=1, item_probs=probs,
                                              threads=threads)
         cpu = {"value": tps, "unit": "triplets/s", "cores": used, "kind": "port",
-               "sample": f"{csteps} optimiser steps of {args.cpu_batch} triplets at the same table shape "
+               "sample": f"{csteps} optimiser steps of {cbatch} triplets at the same table shape "
                          f"(oracle/torch_port.py = the reference's ATen op sequence), {used} threads, "
                          f"{sps * 1e3:.1f} ms/step"}
 
