@@ -308,8 +308,10 @@ static int launch_lean_kernel(const float* U, const float* V, const mfcd_triplet
     const int fit = (int)((227 * 1024) / (smem + 1024));
     per_sm = fit < want ? (fit < 1 ? 1 : fit) : want;
   }
-  // HOT: long-lived CTAs (few flushes per hot row); otherwise a block pass covers 8 warp tiles of 32 triplets
-  const int grid = grid_for(B, HOT ? kLeanBlock * 8 : kLeanBlock, per_sm);
+  // a block pass covers 8 warp tiles of 32 triplets; HOT CTAs take at least two passes (each CTA flushes its hot
+  // images once).  The batch-size sweep showed the earlier 8 passes per CTA starving mid-size batches: 32 CTAs
+  // for 65536 triplets, K1 0.12 ms whatever the batch below 2^20 (profiles/r01_notes.md).
+  const int grid = grid_for(B, HOT ? kLeanBlock * 2 : kLeanBlock, per_sm);
   kern<<<grid, kLeanBlock, smem, st>>>(U, V, rec, perm, start, B, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
