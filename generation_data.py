@@ -10,8 +10,10 @@ reference's triplets bit for bit (parity runs at reference scale).
 
 proximity / variance / top_k (the strategies Runs.ipynb cell 18 sweeps) run on the same
 GPU machinery (per-user top-k lists or an item law + the shared dedup).  The reference's "not used" strategies
-(cluster, user_similarity) and its ten other generators are outside the accelerated path; asking for them
-raises NotImplementedError rather than silently running something else.
+(cluster, user_similarity) and its ten other generators are outside the accelerated path: they are passed through
+to the reference's own host code when ``$MFCD_REFERENCE_PATH`` names a reference checkout (so a Runs.ipynb sweep
+over ``strategies=[..., "cluster", "svd"]`` runs), and raise NotImplementedError otherwise -- never silently
+something else.
 """
 import os
 
@@ -86,11 +88,50 @@ def choose_items_by_svd_projection(X, num_triplets, exclude, rank=10, top_fracti
     return _sampling.sample_svd(X, num_triplets, _as_exclude(exclude), rank=rank, top_fraction=top_fraction)
 
 
-def _outside_hot_path(name):
+_REFERENCE_MODULE = None
+
+
+def _reference_module():
+    """The reference's own generation_data.py, loaded under a private name from $MFCD_REFERENCE_PATH (a checkout
+    of MayeulCassier/Matrix-Factorization-With-Comparison-Data), or None.  Only the strategies and generators that
+    are outside the accelerated path are taken from it ("pass through (host)")."""
+    global _REFERENCE_MODULE
+    if _REFERENCE_MODULE is None:
+        root = os.environ.get("MFCD_REFERENCE_PATH", "")
+        path = os.path.join(root, "generation_data.py") if root else ""
+        if not path or not os.path.isfile(path) or os.path.samefile(path, __file__):
+            _REFERENCE_MODULE = False
+        else:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_mfcd_reference_generation_data", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _REFERENCE_MODULE = mod
+    return _REFERENCE_MODULE or None
+
+
+def _host_matrix(X):
+    """what the reference's host code expects: a CPU float tensor"""
+    if isinstance(X, _GroundTruth):
+        return X.dense().cpu()
+    return X.detach().cpu() if isinstance(X, torch.Tensor) else torch.as_tensor(X)
+
+
+def _outside_hot_path(name, kind="strategy"):
+    """Names outside the B200 hot path: run the reference's host implementation when a reference checkout is
+    importable ($MFCD_REFERENCE_PATH), else raise NotImplementedError (never silently something else)."""
     def fn(*args, **kwargs):
-        raise NotImplementedError(
-            f"{name} is outside the B200 hot path (random / margin / popularity / svd samplers and the 'base' "
-            f"generator are accelerated; see SURVEY.md section 8f)")
+        ref = _reference_module()
+        if ref is None or not hasattr(ref, name):
+            raise NotImplementedError(
+                f"{name} is outside the B200 hot path (random / margin / popularity / svd / proximity / variance / "
+                f"top_k samplers and the 'base' generator are accelerated; see SURVEY.md section 8f). Set "
+                f"MFCD_REFERENCE_PATH to a checkout of the reference to pass it through to the host code.")
+        if kind == "strategy" and args:
+            args = (_host_matrix(args[0]),) + tuple(args[1:])
+            if len(args) > 2 and args[2] is not None and not isinstance(args[2], (set, frozenset)):
+                args = args[:2] + (set(args[2]),) + args[3:]        # a GPU TripletSet -> python set of tuples
+        return getattr(ref, name)(*args, **kwargs)
     fn.__name__ = name
     return fn
 
@@ -164,5 +205,5 @@ for _name in ("generate_low_rank_matrix", "generate_structured_embeddings", "gen
               "generate_correlated_embeddings", "generate_graph_embeddings", "generate_social_embeddings",
               "generate_temporal_embeddings", "generate_hierarchical_embeddings", "generate_gmm_embeddings",
               "generate_clustered_matrix_from_embeddings"):
-    globals()[_name] = _outside_hot_path(_name)
+    globals()[_name] = _outside_hot_path(_name, kind="generator")
 del _name

@@ -237,6 +237,10 @@ k_fwd_bwd_lean(const float* __restrict__ U, const float* __restrict__ V, const m
                 if (!cold_j) smem_add4_at(my_hot + sj * ROWB + it * STEP, nb);
               }
             }
+            // independent thread scheduling gives no ordering between the divergent phases of a warp:
+            // the barrier (and its memory ordering among the participating lanes) makes group ph+1's
+            // read of the image see group ph's write whatever code the compiler emits
+            __syncwarp();
           }
         }
       }

@@ -46,9 +46,14 @@ def _row_stats(model, gt: GroundTruth, s: float, engine=None):
                 rc = lib.mfcd_recon_stats_tc(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar),
                                              ptr(vbar), ptr(stats), ptr(flag), ptr(ws), need.value, st)
                 if rc == 0:
-                    if int(flag.item()) != 0:
+                    if int(flag.item()) == 0:
+                        done = True
+                    elif engine == "tc":
                         raise MfcdError("mfcd_recon_stats_tc: tensor-core pipeline timed out")
-                    done = True
+                    else:       # do not lose a finished training run to a metrics kernel: recompute exactly
+                        import warnings
+                        warnings.warn("mfcd_recon_stats_tc reported a pipeline time-out; recomputing with the "
+                                      "SIMT engine (mfcd_recon_stats)")
                 elif rc != -3 or engine == "tc":          # -3 = MFCD_ERR_UNSUPPORTED -> SIMT engine
                     check(rc, "mfcd_recon_stats_tc")
         if not done:

@@ -63,6 +63,8 @@ class MatrixFactorization(nn.Module):
         if (storage is None and fs is not None and fs.params.is_cuda and self.U.data_ptr() == fs.params.data_ptr()
                 and self.V.data_ptr() == fs.params.data_ptr() + 4 * n * d):
             return fs
+        if storage is None and fs is not None and fs.host_mirror is not None and fs.host_mirror == self._mirror_key():
+            return fs           # U / V are the untouched host copies mirror_to_host() left: the flat state is current
         dev = compute_device(device if device is not None else (self.U.device if self.U.is_cuda else None))
         fs = _FlatState(n, m, d, dev, *(storage or ()))
         with torch.no_grad():
@@ -72,6 +74,22 @@ class MatrixFactorization(nn.Module):
         self.V.data = fs.params[n * d:].view(m, d)
         self._flat = fs
         return fs
+
+    def _mirror_key(self):
+        return (self.U.data_ptr(), self.U._version, self.V.data_ptr(), self.V._version)
+
+    def mirror_to_host(self):
+        """``device='cpu'`` callers get CPU ``model.U`` / ``model.V`` back, like the reference's
+        ``model.to('cpu')`` would leave them (reference-style post-processing against a CPU X keeps working);
+        the flat CUDA state stays attached and is reused as long as the host copies are not modified."""
+        fs = self._flat
+        if fs is None or not fs.params.is_cuda:
+            return
+        n, d, m = fs.n, fs.d, fs.m
+        with torch.no_grad():
+            self.U.data = fs.params[: n * d].view(n, d).cpu()
+            self.V.data = fs.params[n * d:].view(m, d).cpu()
+        fs.host_mirror = self._mirror_key()
 
     def forward(self, u, i, j):
         """Preference probabilities for index tensors u, i, j (inference only: the
@@ -101,6 +119,7 @@ class _FlatState:
         self.state2 = torch.zeros(numel, dtype=torch.float32, device=device)
         self.step = 0
         self.workspace = None
+        self.host_mirror = None
 
     @property
     def U(self):
@@ -159,6 +178,13 @@ def _import_optimizer_state(model, optimizer, fs):
     if isinstance(optimizer, OptimizerSpec) or not hasattr(optimizer, "state"):
         return
     n, d, m = fs.n, fs.d, fs.m
+    if not optimizer.state.get(model.U, None) and not optimizer.state.get(model.V, None):
+        # a fresh torch optimiser starts from zero moments and step 0 (the reference builds a new Adam per
+        # repetition, structure.py:364) -- do not carry over what an earlier optimiser left in the flat state
+        fs.state1.zero_()
+        fs.state2.zero_()
+        fs.step = 0
+        return
     for p, sl in ((model.U, slice(0, n * d)), (model.V, slice(n * d, (n + m) * d))):
         st = optimizer.state.get(p, None)
         if not st:
@@ -270,6 +296,8 @@ def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=1
         train_losses.append(_sum_like_python(step_losses) / len(train_loader))
         val_losses.append(_sum_like_python(vloss) / len(val_loader))      # ZeroDivisionError like the reference
     _export_optimizer_state(model, optimizer, fs, spec)
+    if device is not None and torch.device(device).type == "cpu":
+        model.mirror_to_host()
     return train_losses, val_losses
 
 

@@ -288,17 +288,32 @@ def get_triplets_from_X(X, num_triplets, strategy="random", exclude=None,
     return set(candidates)
 
 
+# generation name -> (generator function in generation_data, what it returns)
+_OTHER_GENERATORS = {
+    "low_rank": ("generate_low_rank_matrix", "USV"), "structured": ("generate_structured_embeddings", "UV"),
+    "svd": ("generate_svd_embeddings", "UV"), "correlated": ("generate_correlated_embeddings", "UV"),
+    "graph": ("generate_graph_embeddings", "UV"), "social": ("generate_social_embeddings", "UV"),
+    "temporal": ("generate_temporal_embeddings", "UV"), "hierarchical": ("generate_hierarchical_embeddings", "UV"),
+    "gmm": ("generate_gmm_embeddings", "UV"), "clustered": ("generate_clustered_matrix_from_embeddings", "X"),
+}
+
+
 def generate_X(n, m, d, device, generation="base", **kwargs):
-    """Ground-truth matrix by scheme (structure.py:590-663).  "base" is the
-    accelerated one; the other ten raise NotImplementedError (outside the hot
-    path), unknown names raise ValueError like the reference."""
+    """Ground-truth matrix by scheme (structure.py:590-663).  "base" is the accelerated one; the other ten are
+    outside the hot path: they run the reference's host generators when $MFCD_REFERENCE_PATH points at a
+    reference checkout and raise NotImplementedError otherwise; unknown names raise ValueError like the reference."""
     if generation == "base":
         return generate_embeddings(n, m, d, device=device)
-    known = ("low_rank", "structured", "svd", "correlated", "graph", "social", "temporal", "hierarchical",
-             "gmm", "clustered")
-    if generation in known:
-        raise NotImplementedError(f"generation scheme '{generation}' is outside the B200 hot path "
-                                  f"(only 'base' is accelerated; SURVEY.md section 8f)")
+    if generation in _OTHER_GENERATORS:
+        fn_name, returns = _OTHER_GENERATORS[generation]
+        fn = getattr(_gen, fn_name)
+        if returns == "USV":
+            U, V, S = fn(n, m, d, rank=kwargs.get("rank", d), device=device)
+            return torch.matmul(torch.matmul(U, torch.diag(S)), V.t())
+        if returns == "X":
+            return fn(n, m, d, device=device)
+        U, V = fn(n, m, d, device=device)
+        return torch.matmul(U, V.t())
     raise ValueError(f"Unknown generation method: {generation}")
 
 

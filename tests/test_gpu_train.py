@@ -172,6 +172,34 @@ def test_run_length_wire_format_round_trip(G, N, n):
         soft.pack_wire(0, 1)
 
 
+@pytest.mark.parametrize("d", [8, 16, 32, 64])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_hot_row_every_lane_group_hits_the_same_row(G, d, flags):
+    """Worst case for the per-warp shared hot image: in EVERY round all lane groups of a warp update the
+    same privatised row (item 0 as i, item 1 as j in every triplet), so a lost update between the groups'
+    turns would show up as a wrong gV[0] / gV[1]."""
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(7 + d)
+    n, m, B = 97, 40, 8192 + 37
+    U = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    V = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    u = np.sort(rng.integers(0, n, B))
+    i = np.zeros(B, np.int64)
+    j = np.ones(B, np.int64)
+    z = rng.integers(0, 2, B).astype(np.float64)
+    store = G.store_from(u, i, j, z)
+    slot = torch.full((m,), -1, dtype=torch.int8, device=G.DEV)
+    slot[0], slot[1], slot[5] = 0, 1, 2
+    items = torch.tensor([0, 1, 5], dtype=torch.int32, device=G.DEV)
+    lo, gUo, gVo = O.loss_and_grads(U, V, u, i, j, z.astype(np.float32))
+    Ud, Vd = G.dev_f32(U), G.dev_f32(V)
+    gU = torch.zeros_like(Ud); gV = torch.zeros_like(Vd); loss = torch.zeros(1, device=G.DEV)
+    check(lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(store.rec), None, 0, B, d, 1.0 / B, ptr(gU), ptr(gV),
+                                      ptr(loss), ptr(slot), ptr(items), 3, flags, current_stream()), "ex")
+    assert abs(loss.item() - lo) < 2e-5 * abs(lo)
+    assert G.rel(gU.cpu().numpy(), gUo) < 2e-5 and G.rel(gV.cpu().numpy(), gVo) < 2e-5
+
+
 @pytest.mark.parametrize("d,hot", [(64, False), (64, True), (32, True), (128, True), (256, False), (16, False)])
 def test_user_grouped_kernel_matches_oracle(G, d, hot):
     """K1 with MFCD_FLAG_USER_GROUPED (one U read / one gU reduction per run of equal users, hottest item
@@ -436,6 +464,48 @@ def test_train_model_api_with_recorded_order(G):
     with pytest.raises(ZeroDivisionError):
         structure.train_model(model, tl.__class__(train_store, 64), TripletLoader(val_store.slice(0, 0), 64), opt, "cpu",
                               num_epochs=1)
+
+
+def test_second_train_model_call_with_a_fresh_optimizer_restarts_the_moments(G):
+    """A fresh torch Adam starts from zero moments and step 0 (the reference builds one per repetition,
+    structure.py:364); the same optimiser object passed again continues.  Also: device='cpu' hands CPU
+    model.U / model.V back while the flat CUDA state stays current."""
+    import structure
+    from mfcd_b200.store import TripletLoader
+    rng = np.random.default_rng(5)
+    n, m, d, N = 40, 30, 8, 640
+    u, i, j = rng.integers(0, n, N), rng.integers(0, m, N), rng.integers(0, m, N)
+    z = rng.integers(0, 2, N).astype(np.float64)
+    store = G.store_from(u, i, j, z)
+    val = G.store_from(u[:64], i[:64], j[:64], z[:64])
+    torch.manual_seed(1)
+    model = structure.MatrixFactorization(n, m, d)
+    U0, V0 = model.U.detach().numpy().copy(), model.V.detach().numpy().copy()
+    batches = O.split_batches(u, i, j, z, 64)
+    lr, wd = 1e-2, 1e-4
+    # oracle (updates its U / V arrays in place): epoch 1 with a fresh Adam, epoch 2 with ANOTHER fresh Adam,
+    # epoch 3 continuing the second one
+    Uo, Vo = U0.copy(), V0.copy()
+    l1, _ = O.train_steps(Uo, Vo, batches, lr, wd)
+    Ua = Uo.copy()
+    l2, st2 = O.train_steps(Uo, Vo, batches, lr, wd)
+    Ub, Vb = Uo.copy(), Vo.copy()
+    l3, _ = O.train_steps(Uo, Vo, batches, lr, wd, state=st2)
+    Uc = Uo.copy()
+    tl, vl = TripletLoader(store, 64), TripletLoader(val, 64)
+    opt1 = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    t1, _ = structure.train_model(model, tl, vl, opt1, "cpu", num_epochs=1)
+    assert not model.U.is_cuda and not model.V.is_cuda                     # handed back on the caller's device
+    assert G.rel(model.U.detach().numpy(), Ua) < 1e-5
+    opt2 = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    t2, _ = structure.train_model(model, tl, vl, opt2, "cpu", num_epochs=1)
+    assert abs(t2[0] - np.mean(l2)) < 1e-5 * abs(np.mean(l2))
+    assert G.rel(model.U.detach().numpy(), Ub) < 1e-5 and G.rel(model.V.detach().numpy(), Vb) < 1e-5
+    assert int(opt2.state[model.U]["step"]) == len(batches)
+    t3, _ = structure.train_model(model, tl, vl, opt2, "cpu", num_epochs=1)  # same optimiser: continues
+    assert abs(t3[0] - np.mean(l3)) < 1e-5 * abs(np.mean(l3))
+    assert G.rel(model.U.detach().numpy(), Uc) < 1e-5
+    assert int(opt2.state[model.U]["step"]) == 2 * len(batches)
 
 
 def test_pack_unpack_gather_roundtrip(G):

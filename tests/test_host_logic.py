@@ -167,3 +167,26 @@ def test_popularity_cdf_and_keys():
         sampling.popularity_cdf(5, "nope")
     assert structure._split_permutation(10, None).tolist() == \
         torch.randperm(10, generator=torch.Generator().manual_seed(42)).tolist()
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/generation_data.py"), reason="no reference checkout here")
+def test_out_of_scope_names_pass_through_to_an_importable_reference(monkeypatch):
+    """cluster / user_similarity and the ten other generators run the reference's own host code when
+    MFCD_REFERENCE_PATH names a checkout (Runs.ipynb cell 16 sweeps "cluster"); without it they raise."""
+    import generation_data as gen
+    monkeypatch.setenv("MFCD_REFERENCE_PATH", "/root/reference")
+    monkeypatch.setattr(gen, "_REFERENCE_MODULE", None)
+    torch.manual_seed(0); np.random.seed(0)
+    X = torch.randn(12, 30)
+    got = structure.get_triplets_from_X(X, 25, strategy="cluster", n_clusters=4)
+    assert isinstance(got, set) and len(got) == 25
+    assert all(0 <= u < 12 and 0 <= i < 30 and 0 <= j < 30 and i != j for u, i, j in got)
+    Xg = structure.generate_X(9, 11, 3, "cpu", generation="gmm")
+    assert tuple(Xg.shape) == (9, 11)
+    Xl = structure.generate_X(9, 11, 3, "cpu", generation="low_rank")
+    assert tuple(Xl.shape) == (9, 11)
+    monkeypatch.setattr(gen, "_REFERENCE_MODULE", None)
+    monkeypatch.delenv("MFCD_REFERENCE_PATH")
+    with pytest.raises(NotImplementedError):
+        structure.get_triplets_from_X(X, 3, strategy="cluster")
+    monkeypatch.setattr(gen, "_REFERENCE_MODULE", None)
