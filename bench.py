@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""Headline benchmark: triplets/s of the fused training step (K1 fwd+bwd -> [all-reduce] -> K3 Adam)
-on synthetic data of BASELINE.json's config shape, with the HBM-roofline fraction of the dominant
-kernel and the reference's CPU path timed beside it.
+"""Headline benchmark: triplets/s of training (K1 fused fwd+bwd -> [gradient exchange] -> K3 Adam) on synthetic
+data of BASELINE.json's config shape, driven THROUGH THE PRODUCT API -- `mfcd_b200.trainer.train_epoch`, the body of
+`structure.train_model`'s epoch loop -- with the roofline numbers of the dominant kernel and the reference's CPU
+path timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on stdout (rank 0).  A "step" is one optimiser step over one batch of
-`--batch` triplets PER GPU (weak scaling): K1 on the local triplets, bucketed NCCL all-reduce of the
-dense gradient when N > 1, fused Adam over all (n+m)*d parameters.  Consecutive steps read different
-batches of a triplet store much larger than L2 (no L2 flush needed for the streamed input; the
-38 MB embedding tables are L2-resident by the nature of the algorithm -- stated in `config`).
+One JSON line on stdout (rank 0).  A "step" is one optimiser step over one batch of `--batch` triplets PER GPU
+(weak scaling; `--scaling strong` fixes the GLOBAL batch instead).  The timed region is ONE EPOCH of K steps over a
+device-resident loader of K x batch triplets, exactly as train_model runs it: the epoch's reshuffle + per-batch user
+grouping (csrc/epoch_batches.cu) is INSIDE the timed region, then per step K1 on the local triplets, the fused
+peer-memory exchange (K9) when N > 1, Adam over all (n+m)*d parameters.  Warm-up = an epoch of W steps over a
+separate loader.  Every step reads fresh triplets of a store much larger than L2; the 38 MB embedding tables are
+L2-resident by the nature of the algorithm (stated in `config`).
+`e2e` = the same epoch through train_epoch over a HostTripletLoader: pinned HOST batches, one host->device copy per
+step inside the timed region, the step's loss read back by the host every step.
 """
 import argparse
 import ctypes as C
@@ -53,6 +58,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-format", default="all", choices=["all", "records16", "wire8", "wire_rle"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch triplets per GPU per step; strong: --batch is the GLOBAL batch, split over the GPUs")
+    ap.add_argument("--no-extra-rooflines", action="store_true", help="skip the K3 / K5 / epoch-batching roofline entries")
     ap.add_argument("--bucket-mb", type=float, default=0.0,
                     help="gradient all-reduce bucket size; 0 = one all-reduce of the whole flat gradient "
                          "(measured faster than 16 MB buckets on NVLink: profiles/r01_notes.md)")
@@ -61,8 +69,8 @@ def parse():
                          "(K9); 'nccl' = NCCL all-reduce + K3")
     ap.add_argument("--multimem", default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--no-hot", action="store_true", help="disable hot-row privatisation in the atomic kernel")
-    ap.add_argument("--no-group", action="store_true",
-                    help="keep the sampler's order inside a batch (default: one user's triplets adjacent)")
+    ap.add_argument("--no-shuffle", action="store_true",
+                    help="walk the store in order (no per-epoch reshuffle / user grouping): isolates the batching cost")
     return ap.parse_args()
 
 
@@ -141,7 +149,26 @@ def cpu_batch_for(TP, cfg, probs, want_batch, steps, budget_s, threads, floor=65
         batch //= 2
 
 
-def reference_arm(args, cfg, rank):
+def batch_split(args, world):
+    """(triplets per GPU per step, global batch)"""
+    if args.scaling == "strong":
+        return max(1, args.batch // world), max(1, args.batch // world) * world
+    return args.batch, args.batch * world
+
+
+def config_dict(args, cfg, world):
+    """The workload description, IDENTICAL for the GPU arm and the reference arm (same keys, same values)."""
+    bl, bg = batch_split(args, world)
+    return {"workload": cfg["workload"], "n_users": cfg["n"], "n_items": cfg["m"], "d": cfg["d"],
+            "batch_per_gpu": bl, "global_batch": bg, "scaling": args.scaling, "scatter_mode": args.mode,
+            "optimizer": "adam(lr=1e-3, wd=1e-5)", "item_distribution": cfg["dist"], "parallelism": f"dp{world}",
+            "entry_point": "mfcd_b200.trainer.train_epoch (the epoch body of structure.train_model): per-epoch "
+                           "reshuffle + user grouping, then K1 -> exchange -> Adam per step",
+            "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB at config 4) are "
+                         "L2-resident by design of the algorithm"}
+
+
+def reference_arm(args, cfg, rank, world):
     """--impl reference: the reference's CPU implementation of the step (oracle/torch_port.py: the same ATen
     ops, pinned bit-exact to the reference by the tests) on the box's host cores, all threads."""
     if rank != 0:
@@ -153,23 +180,34 @@ def reference_arm(args, cfg, rank):
     probs = None
     if cfg["dist"] == "zipf":
         probs = 1.0 / torch.arange(1, cfg["m"] + 1, dtype=torch.float64) ** cfg["alpha"]
+    want = batch_split(args, world)[0]
     # same batch as the GPU arm when steps + warm-up fit ~150 s of host time, else the largest halving that does
-    B = args.cpu_batch if args.cpu_batch > 0 else cpu_batch_for(TP, cfg, probs, args.batch, args.steps + args.warmup,
+    B = args.cpu_batch if args.cpu_batch > 0 else cpu_batch_for(TP, cfg, probs, want, args.steps + args.warmup,
                                                                 150.0, threads)[0]
     tps, sps, used = TP.time_train_steps(cfg["n"], cfg["m"], cfg["d"], B, steps=args.steps, warmup=args.warmup,
                                          item_probs=probs)
     line = {
         "impl": "reference", "metric": "triplets_per_sec", "value": tps, "unit": "triplets/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "n_users": cfg["n"], "n_items": cfg["m"], "d": cfg["d"],
-                   "batch_per_step": B, "optimizer": "adam(lr=1e-3, wd=1e-5)"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, cfg, world),
         "cpu_baseline": {"value": tps, "unit": "triplets/s", "cores": used, "kind": "port",
                          "sample": f"{args.steps} optimiser steps of {B} triplets (torch CPU ops of the reference's "
-                                   f"train step: gather, BCE, autograd backward, dense Adam), {used} threads"},
+                                   f"train step: gather, BCE, autograd backward, dense Adam), {used} threads, one host"},
         "e2e": {"value": tps, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def ncu_facts(key):
+    """per-launch ncu counters of K1 on this workload, committed under profiles/ (None when absent)"""
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    try:
+        with open(path) as f:
+            v = json.load(f).get(key)
+        return v if isinstance(v, dict) else ({"dram_bytes": v} if v else None)
+    except Exception:
+        return None
 
 
 def main():
@@ -179,16 +217,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        reference_arm(args, cfg, rank)
+        reference_arm(args, cfg, rank, world)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import mfcd_b200
     from mfcd_b200 import dist as mdist
-    from mfcd_b200 import sampling
+    from mfcd_b200 import sampling, trainer
     from mfcd_b200._lib import lib, check, ptr, current_stream
-    from mfcd_b200.store import GroundTruth, TripletStore
+    from mfcd_b200.store import GroundTruth, HostTripletLoader, TripletLoader, TripletStore
     from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec
 
     if not torch.cuda.is_available():
@@ -198,232 +237,208 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, m, d = cfg["n"], cfg["m"], cfg["d"]
-    B, K, W = args.batch, args.steps, args.warmup
-    total_steps = K + W
-    shard = B * total_steps                       # every step reads fresh triplets (input >> L2)
+    K, W = args.steps, args.warmup
+    B, B_global = batch_split(args, world)
+    numel = (n + m) * d
 
     # ---- synthetic inputs, created on device before the timed region ---------------------------------
-    torch.manual_seed(1234 + 4)
-    gt_seed = 1234
-    gen = torch.Generator(device=dev); gen.manual_seed(gt_seed)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
     A, _ = torch.linalg.qr(torch.randn(n, d, generator=gen, device=dev))
     Bm, _ = torch.linalg.qr(torch.randn(m, d, generator=gen, device=dev))
     gt = GroundTruth(A=A, B=Bm, scale=math.sqrt(n * m) / (2 * math.sqrt(d)), device=dev)
-    keys = torch.empty(shard, dtype=torch.int64, device=dev)
-    seed = 42 + 1000 * rank                        # per-GPU disjoint Philox streams
-    if cfg["dist"] == "zipf":
-        cdf = torch.from_numpy(sampling.popularity_cdf(m, "zipf", cfg["alpha"])).to(dev)
-        check(lib.mfcd_sample_popularity(n, m, shard, seed, 0, ptr(cdf), ptr(keys), current_stream()), "sample")
-    else:
-        check(lib.mfcd_sample_random(n, m, shard, seed, 0, ptr(keys), current_stream()), "sample")
-    bad = keys == -1                               # i == j candidates: redirect to a valid pair
-    keys[bad] = 1
-    store = sampling.btl_records(gt, sampling.TripletSet(keys, n, m), scale=1.0, K=1, soft=False, seed=seed)
-    del keys, bad
-    if not args.no_group:
-        # batch layout: inside every batch one user's triplets are adjacent (same batches, same sums);
-        # done once, before the timed region, like the sampling itself
-        store.group_by_user(B)
-    k1_flags = store.k1_flags(B)
+    cdf = torch.from_numpy(sampling.popularity_cdf(m, "zipf", cfg["alpha"])).to(dev) if cfg["dist"] == "zipf" else None
 
-    torch.manual_seed(7)                           # identical replicas on every rank
+    def make_store(count, seed):
+        keys = torch.empty(count, dtype=torch.int64, device=dev)
+        if cdf is not None:
+            check(lib.mfcd_sample_popularity(n, m, count, seed, 0, ptr(cdf), ptr(keys), current_stream()), "sample")
+        else:
+            check(lib.mfcd_sample_random(n, m, count, seed, 0, ptr(keys), current_stream()), "sample")
+        keys[keys == -1] = 1                        # i == j candidates: redirect to a valid pair
+        return sampling.btl_records(gt, sampling.TripletSet(keys, n, m), scale=1.0, K=1, soft=False, seed=seed)
+
+    seed = 42 + 1000 * rank                         # per-GPU disjoint Philox streams
+    store = make_store(B * K, seed)                 # the timed epoch: K batches per GPU
+    warm_store = make_store(B * W, seed + 500) if W > 0 else None
+    shuffle = not args.no_shuffle
+    loader = TripletLoader(store, batch_size=B_global, shuffle=shuffle, shuffle_rng="device")
+    warm_loader = TripletLoader(warm_store, batch_size=B_global, shuffle=shuffle, shuffle_rng="device") if W else None
+    # once per dataset, like the sampling itself: the user-sorted layout the epoch multisplit reads, and the
+    # item-frequency count behind hot-row privatisation (timed here, reported under `setup`)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if shuffle:
+        loader._user_sorted()
+        if warm_loader is not None:
+            warm_loader._user_sorted()
+    torch.cuda.synchronize()
+    t_sort = time.perf_counter() - t0
+    if args.no_hot:
+        store._hot_cache = {(m, d, B): None}
+        if warm_store is not None:
+            warm_store._hot_cache = {(m, d, B): None}
+    t0 = time.perf_counter()
+    hot = store.hot_items(m, d, B)
+    torch.cuda.synchronize()
+    t_hot = time.perf_counter() - t0
+
+    torch.manual_seed(7)                            # identical replicas on every rank
     model = MatrixFactorization(n, m, d)
-    exchange = None
-    if world > 1 and args.dp_backend == "peer":
-        exchange = mdist.PeerExchange((n + m) * d, dev,
-                                      use_multimem={"auto": "auto", "on": True, "off": False}[args.multimem])
-        fs = model.flat_state(dev, storage=exchange.storage())
-    else:
-        fs = model.flat_state(dev)
     spec = OptimizerSpec.adam(lr=1e-3, weight_decay=1e-5)
     mode = 0 if args.mode == "atomic" else 1
-    engine = mdist.CudaEngine(fs, store, None, spec, mode, use_hot=not args.no_hot)
-    hot = store.hot_items(m, d, B) if (mode == 0 and not args.no_hot) else None
-    hot_args = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
-    plan = mdist.PartitionedPlan([shard] * world, B, rank)
-    losses = torch.zeros(total_steps, dtype=torch.float32, device=dev)
-    numel = (n + m) * d
-    bucket_elems = int(args.bucket_mb * (1 << 20) / 4) if args.bucket_mb > 0 else numel
-    n_buckets = len(mdist.bucket_bounds(numel, bucket_elems)) if world > 1 else 1
-    nU = n * d
-
-    def one_step(k, rec=None, start=None, ev=None, flags=None):
-        """K1 -> (all-reduce) -> K3 for global step k."""
-        s, bl, bg = plan.local_range(k)
-        flags = k1_flags if flags is None else flags
-        if rec is not None:
-            s = start
-        if ev is not None:
-            ev[0].record()
-        if mode == 0:
-            check(lib.mfcd_triplet_fwd_bwd_ex(ptr(fs.params), ptr(fs.params[nU:]),
-                                              ptr(rec if rec is not None else store.rec), None, s, bl, d, 1.0 / bg,
-                                              ptr(fs.grads), ptr(fs.grads[nU:]), ptr(losses[k:k + 1]), *hot_args,
-                                              flags, current_stream()), "k1")
-        else:
-            if rec is not None:
-                engine.store = TripletStore(rec)
-            engine.fwd_bwd(s, bl, bg, losses[k:k + 1])
-            engine.store = store
-        if ev is not None:
-            ev[1].record()
-        g = fs.grads
-        if exchange is not None:
-            exchange.step(fs, spec, fs.step + 1)
-        elif world > 1 and n_buckets == 1:
-            dist.all_reduce(g)
-            engine.update(0, numel, fs.step + 1)
-        elif world > 1:
-            bounds = mdist.bucket_bounds(numel, bucket_elems)
-            works = [dist.all_reduce(g[a:b], async_op=True) for a, b in bounds]
-            for (a, b), w in zip(bounds, works):
-                w.wait()
-                engine.update(a, b, fs.step + 1)
-        else:
-            engine.update(0, numel, fs.step + 1)
-        fs.step += 1
+    dp = None
+    if world > 1:
+        if args.multimem != "auto":
+            os.environ["MFCD_DP_MULTIMEM"] = args.multimem
+        dp = mdist.DataParallel.attach(model, dev, spec, backend=args.dp_backend)
+        fs = dp.fs
+    else:
+        fs = model.flat_state(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ------------------------------------------------------------------------
-    for k in range(W):
-        one_step(k)
-    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # ---- device-resident timing: one epoch through trainer.train_epoch --------------------------------
+    if warm_loader is not None:
+        trainer.train_epoch(fs, warm_loader, spec, mode, dp=dp)
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local_rank) if rank == 0 else None     # NVML init happens BEFORE the barrier (it takes ms)
     barrier()
     barrier()
+    check(lib.mfcd_profile_k1(1), "profile")
     wall0 = time.perf_counter()
     t_begin.record()
-    for k in range(K):
-        one_step(W + k, ev=k1_ev[k])
+    step_losses = trainer.train_epoch(fs, loader, spec, mode, dp=dp)
     t_end.record()
     barrier()
     wall1 = time.perf_counter()
+    check(lib.mfcd_profile_k1(0), "profile")
     clk = clocks.stop(wall0, wall1) if clocks else None
+    k1_tot, k1_n = C.c_double(0), C.c_int64(0)
+    check(lib.mfcd_profile_k1_read(C.byref(k1_tot), C.byref(k1_n)), "profile read")
+    assert k1_n.value == K and len(step_losses) == K, (k1_n.value, len(step_losses), K)
     ms = t_begin.elapsed_time(t_end)
-    k1_ms = sum(a.elapsed_time(b) for a, b in k1_ev) / K
+    k1_ms = k1_tot.value / K
     t = torch.tensor([ms, k1_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, k1_ms = float(t[0]), float(t[1])
-    final_loss = float(losses[W + K - 1].item())
+    final_loss = float(step_losses[-1])             # global batch mean (all-reduced over the ranks by dp_epoch)
     value = world * B * K / (ms * 1e-3)
 
-    # ---- end to end: host buffers, H2D of every batch + D2H of the loss inside the timed region ---------
+    # the epoch's reshuffle + grouping alone (same call the epoch makes), for the breakdown
+    batching_ms = None
+    if shuffle:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        loader.epoch_records(B)
+        torch.cuda.synchronize()
+        evs[0].record()
+        loader.epoch_records(B)
+        evs[1].record()
+        torch.cuda.synchronize()
+        batching_ms = evs[0].elapsed_time(evs[1])
+
+    # ---- end to end: host batches through the same API, H2D of every batch + D2H of the loss per step --
     e2e = None
     e2e_formats = {}
     if not args.no_e2e:
-        dbuf = [torch.empty((B, 4), dtype=torch.int32, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-
-        def stage(fmt):
-            """-> (per-step pinned host tensors, per-step device staging buffers or None, unpack fn, bytes/step)"""
-            if fmt == "records16":          # the 16-byte records as they sit in HBM
-                host = torch.empty((total_steps, B, 4), dtype=torch.int32).pin_memory()
-                host.copy_(store.rec.view(total_steps, B, 4).cpu())
-                return [host[k] for k in range(total_steps)], None, None, B * 16
-            if fmt == "wire8":              # 8-byte records (hard labels)
-                host = torch.empty((total_steps, B), dtype=torch.int64).pin_memory()
-                host.copy_(store.pack8().view(total_steps, B).cpu())
-                wire = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
-                return [host[k] for k in range(total_steps)], wire, \
-                    (lambda w, out: TripletStore.from_packed8(w, out)), B * 8
-            # run-length format of a user-grouped batch: ~4.1 bytes per triplet + 4 per run
-            words = [store.pack_wire(k * B, B) for k in range(total_steps)]
-            cap = max(w.numel() for w in words)
-            host = torch.empty((total_steps, cap), dtype=torch.int32).pin_memory()
-            hk = []
-            for k, w in enumerate(words):
-                host[k, : w.numel()].copy_(w.cpu())
-                hk.append(host[k, : w.numel()])
-            wire = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
-            return hk, wire, "k1-reads-wire", sum(w.numel() for w in words) * 4 // total_steps
+        # what a host-side loader owns: the epoch's records in a shuffled order, raw 16-byte records
+        with torch.cuda.device(dev):
+            order = torch.randperm(B * K, device=dev)
+            host_rec = store.rec[order].cpu().numpy()
+            del order
+        pack_times = {}
 
         def run_format(fmt):
-            host, wire, unpack, nbytes = stage(fmt)
-            # the staging loop above has just WRITTEN the pinned batches with the CPU: the last ones are still
-            # dirty in the CPU caches, and a DMA read that has to snoop them runs at ~8 GB/s instead of ~50
-            # (measured: only the last two batches of a run were slow).  Push them out to DRAM first.
+            t0 = time.perf_counter()
+            hl = HostTripletLoader.from_records(host_rec, B, fmt=fmt)
+            pack_times[fmt] = time.perf_counter() - t0
+            hl.hot = hot
+            warm = HostTripletLoader(hl.batches[:max(W, 1)], hl.sizes[:max(W, 1)], fmt=fmt, user_grouped=hl.user_grouped)
+            warm.hot = hot
+            # the staging code has just WRITTEN the pinned batches with the CPU: the last ones are still dirty in
+            # the CPU caches, and a DMA read that has to snoop them runs at ~8 GB/s instead of ~50.  Push them out.
             evict = torch.empty(1 << 28, dtype=torch.int32)
             evict.fill_(1)
             del evict
-            direct = unpack == "k1-reads-wire"       # K1 decodes the run-length batch itself (MFCD_FLAG_WIRE_RLE)
-            ready = [torch.cuda.Event(), torch.cuda.Event()]
-            freed = [torch.cuda.Event(), torch.cuda.Event()]
-            losses.zero_()
-
-            def upload(k):
-                b = k % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[b])
-                    if wire is None:
-                        dbuf[b].copy_(host[k], non_blocking=True)
-                    else:
-                        wire[b][: host[k].numel()].copy_(host[k], non_blocking=True)
-                        if not direct:
-                            unpack(wire[b], dbuf[b])                 # unpack kernel on the copy stream
-                    ready[b].record(copy_stream)
-
-            loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-            done = [torch.cuda.Event(), torch.cuda.Event()]
-
-            def run(first, count):
-                out, pending = 0.0, None
-                for b in range(2):
-                    freed[b].record()
-                upload(first)
-                for k in range(first, first + count):
-                    if k + 1 < first + count:
-                        upload(k + 1)               # next batch's copy overlaps this batch's compute
-                    torch.cuda.current_stream().wait_event(ready[k % 2])
-                    if direct:
-                        one_step(k, rec=wire[k % 2], start=0, flags=k1_flags | 2)
-                    else:
-                        one_step(k, rec=dbuf[k % 2], start=0)
-                    freed[k % 2].record()
-                    # D2H of the step's loss (4 bytes), every step; the host reads it once the NEXT step is
-                    # queued, so the GPU does not idle while python launches
-                    loss_host[k % 2: k % 2 + 1].copy_(losses[k:k + 1], non_blocking=True)
-                    done[k % 2].record()
-                    if pending is not None:
-                        done[pending % 2].synchronize()
-                        out = float(loss_host[pending % 2])
-                    pending = k
-                done[pending % 2].synchronize()
-                return float(loss_host[pending % 2])
-            run(0, W)
+            trainer.train_epoch(fs, warm, spec, mode, dp=dp)
             barrier()
             w0 = time.perf_counter()
-            last = run(W, K)
+            ls = trainer.train_epoch(fs, hl, spec, mode, dp=dp)
             barrier()
             w1 = time.perf_counter()
             te = torch.tensor([w1 - w0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            out = {"value": world * B * K / float(te[0]), "unit": "triplets/s",
-                   "h2d_bytes_per_step": world * nbytes, "d2h_bytes_per_step": world * 4, "last_loss": last}
-            return out
+            return {"value": world * B * K / float(te[0]), "unit": "triplets/s",
+                    "h2d_bytes_per_step": int(world * hl.bytes_per_step()), "d2h_bytes_per_step": world * 4,
+                    "last_loss": float(ls[-1])}
 
-        formats = ["records16", "wire8"] + (["wire_rle"] if (k1_flags and m <= 65536 and mode == 0 and d % 4 == 0) else [])
-        if "wire_rle" in formats and total_steps * B * 16 > (4 << 30):
-            formats = ["wire_rle"]      # long runs: do not pin gigabytes of host memory for the comparison formats
+        formats = ["records16", "wire8"]
+        if m <= 65536 and mode == 0 and d % 4 == 0 and d in (4, 8, 16, 32, 64, 128, 256, 384, 512) and B * K <= (1 << 26):
+            formats.append("wire_rle")
         for fmt in (formats if args.e2e_format == "all" else [args.e2e_format]):
             e2e_formats[fmt] = run_format(fmt)
-        best = "wire_rle" if "wire_rle" in e2e_formats else ("wire8" if "wire8" in e2e_formats else list(e2e_formats)[0])
-        e2e = dict(e2e_formats[best])
-        e2e["format"] = best
-        e2e["how"] = ("pinned host batches in the '%s' staging format -> cudaMemcpyAsync (double-buffered on a copy "
-                      "stream; wire8 adds an unpack kernel) -> K1 -> exchange -> update -> the step's loss copied back "
-                      "and read by the host every step (the read of step k overlaps the launch of step k+1); wall "
-                      "clock, max over ranks. records16 = the 16-byte HBM records; wire8 = 8-byte hard-label records; wire_rle = "
-                      "run-length format of a user-grouped batch, decoded by K1 itself (include/mfcd_b200.h: mfcd_pack_wire, "
-                      "MFCD_FLAG_WIRE_RLE)" % best)
-        e2e["other_formats"] = {f: {"value": v["value"], "h2d_bytes_per_step": v["h2d_bytes_per_step"]}
-                                for f, v in e2e_formats.items() if f != best}
+        head = "records16" if "records16" in e2e_formats else list(e2e_formats)[0]
+        e2e = dict(e2e_formats[head])
+        e2e["format"] = head
+        e2e["how"] = ("trainer.train_epoch over a HostTripletLoader: the epoch's batches sit in pinned HOST memory as raw "
+                      "16-byte records in a shuffled order (what a host loader hands over; no packing anywhere) -> one "
+                      "cudaMemcpyAsync per step on a copy stream (double-buffered) -> K1 -> exchange -> Adam -> the "
+                      "step's loss copied back and read by the host every step (one step behind the launches); wall "
+                      "clock, max over ranks.  other_formats: the same loop fed from batches the HOST packed beforehand "
+                      "(hostpack.py, numpy) -- wire8 = 8-byte hard-label records + an unpack kernel, wire_rle = "
+                      "run-length words of user-grouped batches decoded by K1; their packing is NOT in the timed region "
+                      "and costs host_pack_s per epoch on one core (a pack-once, stream-every-epoch format)")
+        e2e["other_formats"] = {f: {"value": v["value"], "h2d_bytes_per_step": v["h2d_bytes_per_step"],
+                                    "host_pack_s_per_epoch": pack_times[f]}
+                                for f, v in e2e_formats.items() if f != head}
+
+    # ---- secondary rooflines (kernels timed alone, after the run) ---------------------------------------
+    peak, peak_src = measured_peak()
+    extra = []
+    if rank == 0 and not args.no_extra_rooflines:
+        def timed(fn, reps=20):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        # K3: dense Adam over private buffers of the same size (32 bytes per element)
+        bufs = [torch.zeros(numel, dtype=torch.float32, device=dev) for _ in range(4)]
+        t_adam = timed(lambda: check(lib.mfcd_adam_update(ptr(bufs[0]), ptr(bufs[1]), ptr(bufs[2]), ptr(bufs[3]), numel, 1e-3,
+                                                          0.9, 0.999, 1e-8, 1e-5, 1, 1, current_stream()), "adam"))
+        extra.append({"kernel": "k_adam (K3 dense Adam + grad clear)", "bound": "hbm", "achieved": 32 * numel / (t_adam * 1e-3) / 1e9,
+                      "peak": peak, "unit": "GB/s", "frac": 32 * numel / (t_adam * 1e-3) / 1e9 / peak, "ms": t_adam,
+                      "bytes_per_launch": 32 * numel,
+                      "note": "4 x 38 MB working set: partly L2-resident between launches, so frac can exceed 1"})
+        del bufs
+        if batching_ms:
+            nb = B * K
+            extra.append({"kernel": "k_epoch_count + scan + k_epoch_scatter (per-epoch reshuffle + user grouping)",
+                          "bound": "hbm", "achieved": 32 * nb / (batching_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": 32 * nb / (batching_ms * 1e-3) / 1e9 / peak, "ms": batching_ms, "bytes_per_launch": 32 * nb,
+                          "share_of_epoch": batching_ms / ms})
+        # K5: reconstruction statistics on a dense X of 8192 x 20480 (671 MB), d of this config
+        try:
+            from mfcd_b200 import metrics
+            xn, xm = 8192, 20480
+            km = MatrixFactorization(xn, xm, d)
+            X = torch.randn(xn, xm, device=dev)
+            g5 = GroundTruth(X=X, device=dev)
+            metrics._row_stats(km, g5, 1.0)
+            t_k5 = timed(lambda: metrics._row_stats_device(km, g5, 1.0), reps=5)
+            extra.append({"kernel": "K5 reconstruction statistics (tcgen05/TMA engine where eligible)", "bound": "hbm",
+                          "achieved": 4 * xn * xm / (t_k5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": 4 * xn * xm / (t_k5 * 1e-3) / 1e9 / peak, "ms": t_k5, "bytes_per_launch": 4 * xn * xm,
+                          "shape": [xn, xm, d]})
+            del X, g5, km
+        except Exception as ex:       # a secondary line must not take the headline down
+            extra.append({"kernel": "K5", "error": str(ex)[:200]})
 
     # ---- CPU baseline (rank 0, N == 1 only) -------------------------------------------------------------
     cpu = None
@@ -449,45 +464,45 @@ def main():
                          f"{sps * 1e3:.1f} ms/step"}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         bytes_per_triplet = 16 + 24 * d
         achieved = bytes_per_triplet * B / (k1_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(f"{args.config}_{args.mode}_B{B}")
-            except Exception:
-                traffic = None
+        facts = ncu_facts(f"{args.config}_{args.mode}_B{B}") or {}
+        traffic = facts.get("dram_bytes")
+        inst = facts.get("warp_instructions")
+        sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+        config = config_dict(args, cfg, world)
+        config.update({
+            "dp_exchange": ("none" if world == 1 else
+                            ("peer-memory fused K9, in-kernel flags" + (" (multimem)" if dp.exchange.multimem else " (p2p)")
+                             if dp.exchange is not None else "nccl all-reduce + K3")),
+            "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
+            "batch_layout": ("per-epoch device shuffle; every batch grouped by user (epoch_batches.cu), inside the "
+                             "timed region" if shuffle else "store order, no reshuffle")})
         line = {
             "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "n_users": n, "n_items": m, "d": d, "batch_per_gpu": B,
-                       "global_batch": B * world, "scatter_mode": args.mode, "optimizer": "adam(lr=1e-3, wd=1e-5)",
-                       "item_distribution": cfg["dist"], "parallelism": f"dp{world}",
-                       "dp_exchange": ("none" if world == 1 else ("peer-memory fused K9" + (" (multimem)" if exchange.multimem else " (p2p)")
-                                                                  if exchange is not None else "nccl all-reduce + K3")),
-                       "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
-                       "batch_layout": ("grouped by user inside each batch" if k1_flags else "sampler order"),
-                       "l2_policy": "each step streams a fresh batch from a store >> L2; tables (38 MB) are L2-resident "
-                                    "by design of the algorithm"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_lean (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_triplet": bytes_per_triplet, "k1_ms": k1_ms,
-                         "limiter": "ncu (profiles/r01c_ncu_k1_lean_full_summary.json): issue slots 66 %, LSU data pipe "
-                                    "60 %, L2 12 %, DRAM 4 % -- the 38 MB tables and their gradients are served by L1/L2",
+                         "dram_frac": (traffic / (k1_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "issue_frac": (inst / (148 * 4 * sm_mhz * 1e6 * k1_ms * 1e-3)) if inst else None,
+                         "limiter": "issue slots / LSU data pipe (the 38 MB tables and their gradients are L1/L2-resident); "
+                                    "NOT HBM: dram_frac is the measured DRAM share, issue_frac the warp-instruction issue share",
                          "k1_share_of_step": k1_ms / (ms / K),
-                         "note": "achieved = (16 + 24 d) algorithmic bytes x triplets / K1 time (SURVEY 8d). The "
-                                 "embedding tables and their gradients (2 x 38.4 MB at config 4) stay L2-resident, so "
-                                 "most of those bytes are served by L2: `traffic` is the DRAM bytes per launch ncu "
-                                 "measured (profiles/), and frac > 1 means faster than streaming the same bytes "
-                                 "from HBM, not skipped work (parity tests cover this exact kernel)."},
+                         "note": "achieved/frac follow SURVEY 8(d): (16 + 24 d) ALGORITHMIC bytes x triplets / K1 time vs "
+                                 "the measured HBM copy peak.  Most of those bytes are served by L2 (frac > 1 is not an HBM "
+                                 "statement): dram_frac = ncu dram bytes per launch / K1 time / peak; issue_frac = ncu "
+                                 "warp instructions per launch / (148 SMs x 4 schedulers x SM clock x K1 time)."},
+            "rooflines_other": extra,
+            "breakdown_ms_per_epoch": {"epoch": ms, "k1_total": k1_ms * K, "reshuffle_and_grouping": batching_ms,
+                                       "steps": K},
+            "setup": {"user_sort_s_once_per_dataset": t_sort, "hot_item_count_s_once_per_dataset": t_hot},
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
-            # launches of this repo's kernels inside the timed region: per step K1 + (K3 per bucket | K9 exchange);
-            # deterministic mode: forward + loss-finish + 3 x (keys, meta, segmented reduce, 2 fix-ups) + update
-            "gpu_launches": K * ((1 if mode == 0 else 17) + (1 if exchange is not None else n_buckets)),
+            # launches of this repo's kernels inside the timed region: per step K1 + (K3 | K9 exchange); per epoch the
+            # reshuffle (count, 3 scan kernels, scatter); deterministic mode: 17 launches per step
+            "gpu_launches": K * ((1 if mode == 0 else 17) + 1) + (5 if shuffle else 0),
             "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)

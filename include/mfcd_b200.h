@@ -62,6 +62,12 @@ int mfcd_abi_version(void);
 const char* mfcd_last_error(void);
 int mfcd_device_sm_count(int* out);
 
+/* Live timing of K1 (mfcd_triplet_fwd_bwd*, also inside mfcd_train_epoch): while enabled (per calling thread),
+ * every K1 launch is bracketed by a CUDA event pair on its own stream.  mfcd_profile_k1_read synchronises those
+ * events, returns the summed duration and the number of launches, and forgets them. */
+int mfcd_profile_k1(int32_t enable);
+int mfcd_profile_k1_read(double* total_ms, int64_t* launches);
+
 /* ---- data staging ---------------------------------------------------------- */
 /* int64 u,i,j + float64 z columns (what the reference's DataLoader yields,
  * structure.py:846) -> 16-byte records. */
@@ -90,6 +96,23 @@ int mfcd_unpack_wire(const uint32_t* wire, int64_t B, mfcd_triplet* out, void* s
  * (replaces RandomSampler + default_collate, structure.py:738, :845). */
 int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N, mfcd_triplet* out,
                          void* stream);
+
+/* ---- epoch batching: the epoch reshuffle and the per-batch user grouping in one streaming pass -------------
+ * Replaces RandomSampler + default_collate for one epoch (structure.py:738, :845) at throughput batch sizes.
+ * Record r of the store has epoch position pos(r): pos[r] when `pos` is given (int32, the INVERSE of the epoch
+ * permutation: see mfcd_invert_perm), else a keyed bijection of [0, N) evaluated on the fly (8-round alternating
+ * Feistel network over ceil(log2 N) bits, cycle walking; mfcd_epoch_positions writes the same values out).
+ * Batch b = { r : pos(r) / B == b } -- exactly the batches a loader that walks the permutation in chunks of B
+ * forms (every batch has B members, the last one the remainder).  out[] receives batch 0, batch 1, ... each in
+ * STORE order (stable), so a store sorted by user yields user-grouped batches (MFCD_FLAG_USER_GROUPED) for free.
+ * At most mfcd_epoch_max_batches() batches per epoch and N < 2^31, else MFCD_ERR_UNSUPPORTED (callers then gather
+ * through an explicit permutation, mfcd_gather_triplets).  out must not alias rec. */
+int mfcd_epoch_max_batches(int32_t* out);
+int mfcd_epoch_positions(int64_t N, uint64_t seed, int32_t* pos, void* stream);
+int mfcd_invert_perm(const int32_t* perm, int64_t N, int32_t* pos, void* stream);
+int mfcd_epoch_batches_workspace(int64_t N, int64_t B, size_t* bytes);
+int mfcd_epoch_batches(const mfcd_triplet* rec, int64_t N, int64_t B, const int32_t* pos, uint64_t seed,
+                       mfcd_triplet* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K1: fused forward + BCE + backward, atomic scatter --------------------
  * Replaces structure.py:848-850 (model forward :787-795, F.binary_cross_entropy,
@@ -178,6 +201,19 @@ int mfcd_dp_fused_adam(const uint64_t* peer_grads, const uint64_t* peer_params, 
                        uint64_t mc_params, int32_t rank, int32_t world, int64_t numel, float* m, float* v,
                        float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                        void* stream);
+
+/* The same exchange with the synchronisation INSIDE the kernel (no host-visible barriers, no separate gradient
+ * memset): peer_flags[q] = address of rank q's flag array (16 uint32, zero-initialised once, peer-mapped like the
+ * other buffers): words [0,8) "gradients of rank r ready up to sequence number s", words [8,16) "rank r done with
+ * my buffers up to s".  The kernel publishes ready[rank] = seq to every rank, waits for all ready[] >= seq, does
+ * reduce-scatter + Adam + all-gather, writes zeros over the gradient slice it consumed in every rank's buffer,
+ * then its last CTA publishes done[rank] = seq and waits for all done[] >= seq before exiting.  `seq` must grow by
+ * one per call, identically on all ranks, starting at 1.  cta_counter: one zeroed device word reused across
+ * calls.  *error (device) becomes 1 if a bounded spin timed out (results are then invalid). */
+int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_flags,
+                            uint64_t mc_grads, uint64_t mc_params, int32_t rank, int32_t world, int64_t numel,
+                            float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            int64_t step, uint32_t seq, uint32_t* cta_counter, int32_t* error, void* stream);
 
 /* ---- one training epoch, launched from C ------------------------------------
  * The inner loop of train_model (structure.py:845-852) for one epoch on one GPU:

@@ -54,6 +54,8 @@ SZ = C.c_size_t
 # (tests/test_abi.py parses the header and checks both directions).
 SIGNATURES = {
     "mfcd_device_sm_count": [C.POINTER(C.c_int)],
+    "mfcd_profile_k1": [I32],
+    "mfcd_profile_k1_read": [C.POINTER(C.c_double), C.POINTER(I64)],
     "mfcd_pack_triplets": [P, P, P, P, I64, P, P],
     "mfcd_unpack_triplets": [P, I64, P, P, P, P, P],
     "mfcd_pack_triplets8": [P, I64, P, P, P],
@@ -62,6 +64,11 @@ SIGNATURES = {
     "mfcd_pack_wire": [P, I64, P, I64, P, P, SZ, P],
     "mfcd_unpack_wire": [P, I64, P, P],
     "mfcd_gather_triplets": [P, P, I64, P, P],
+    "mfcd_epoch_max_batches": [C.POINTER(I32)],
+    "mfcd_epoch_positions": [I64, U64, P, P],
+    "mfcd_invert_perm": [P, I64, P, P],
+    "mfcd_epoch_batches_workspace": [I64, I64, C.POINTER(SZ)],
+    "mfcd_epoch_batches": [P, I64, I64, P, U64, P, P, SZ, P],
     "mfcd_triplet_fwd_bwd": [P, P, P, P, I64, I64, I32, F32, P, P, P, P],
     "mfcd_max_hot_items": [I32, C.POINTER(I32)],
     "mfcd_triplet_fwd_bwd_hot": [P, P, P, P, I64, I64, I32, F32, P, P, P, P, P, I32, P],
@@ -75,6 +82,8 @@ SIGNATURES = {
     "mfcd_dp_shard_range": [I64, I32, I32, C.POINTER(I64), C.POINTER(I64)],
     "mfcd_dp_fused_adam": [C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32, F32, F32, F32, F32,
                            I64, P],
+    "mfcd_dp_fused_adam_sync": [C.POINTER(U64), C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32,
+                                F32, F32, F32, F32, I64, C.c_uint32, P, P, P],
     "mfcd_train_epoch": [C.POINTER(EpochArgs)],
     "mfcd_train_epoch_workspace": [C.POINTER(EpochArgs), C.POINTER(SZ)],
     "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P],

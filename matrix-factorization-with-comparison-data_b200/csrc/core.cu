@@ -1,7 +1,24 @@
 // Library plumbing: error strings, device info, record packing / gathering.
+#include <vector>
 #include "common.cuh"
+#include "internal.h"
 
 namespace mfcd {
+
+// ---- K1 launch timing (mfcd_profile_k1): CUDA event pairs on the launching stream ------------------------
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+K1Timer::K1Timer(cudaStream_t st) : st_(st), on_(g_prof_on) {
+  if (!on_) return;
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on_ = false; return; }
+  g_prof_events.emplace_back(a, b);
+  cudaEventRecord(a, st_);
+}
+K1Timer::~K1Timer() {
+  if (on_) cudaEventRecord(g_prof_events.back().second, st_);
+}
 
 static thread_local char g_err[512] = "";
 
@@ -102,6 +119,30 @@ extern "C" int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_tri
   MFCD_REQUIRE(packed && out, "mfcd_unpack_triplets8: NULL pointer");
   k_unpack8<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(packed), N, out);
   MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_profile_k1(int32_t enable) {
+  g_prof_on = enable != 0;
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_profile_k1_read(double* total_ms, int64_t* launches) {
+  MFCD_REQUIRE(total_ms && launches, "mfcd_profile_k1_read: NULL pointer");
+  double tot = 0.0;
+  int64_t n = 0;
+  for (auto& ev : g_prof_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_prof_events.clear();
+  *total_ms = tot;
+  *launches = n;
   return MFCD_OK;
 }
 

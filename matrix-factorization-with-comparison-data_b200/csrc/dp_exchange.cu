@@ -100,9 +100,184 @@ k_dp_fused_adam(PeerTable grads, PeerTable params, const float* __restrict__ mc_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// K9 with in-kernel synchronisation (the default): no host-visible barrier and no separate gradient memset.
+//
+//   flags (peer-mapped, one array per rank):  ready[q] = sequence number of the last step for which rank q's
+//   gradients are final;  done[q] = last step for which rank q has finished reading MY gradients, writing MY
+//   parameter replica and clearing its slice of MY gradient buffer.  Sequence numbers only grow, so nothing is
+//   ever reset.
+//
+//   start:  CTA 0 publishes ready[rank] = seq into every rank's flag array (K1 of this step has completed in
+//           stream order, its reductions are in this GPU's L2 where peer loads are served);
+//           every CTA waits until all ranks' ready[] >= seq (acquire, system scope);
+//   body:   reduce-scatter of the owned slice -> Adam -> all-gather, and the owner writes ZEROS over the slice it
+//           has just consumed in every rank's gradient buffer (so the next K1 accumulates into a clean buffer);
+//   end:    the last CTA to finish publishes done[rank] = seq everywhere and waits for every rank's done[] >= seq
+//           before it exits: the kernel -- and with it the next K1 in the stream -- cannot complete / start
+//           before all replicas are written and all gradient slices are cleared.
+//   Spins are bounded (~4 s of SM clocks): on time-out *error is set and the kernel leaves instead of hanging.
+// ---------------------------------------------------------------------------------------------------------
+struct FlagTable { uint32_t* p[kMaxPeers]; };      // p[q][0..8) = ready[], p[q][8..16) = done[]  (rank q's array)
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until word >= seq (wrap-safe compare); false on time-out
+__device__ __forceinline__ bool spin_until(const uint32_t* word, uint32_t seq) {
+  const long long t0 = clock64();
+  while ((int32_t)(ld_acquire_sys(word) - seq) < 0) {
+    if (clock64() - t0 > 8000000000ll) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+template <bool MULTIMEM>
+__global__ void __launch_bounds__(256, 4)
+k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* __restrict__ mc_grads,
+                     float* __restrict__ mc_params, int rank, int world, int64_t begin, int64_t end,
+                     float* __restrict__ m, float* __restrict__ v, AdamK s, uint32_t seq,
+                     unsigned int* __restrict__ cta_counter, int* __restrict__ error) {
+  uint32_t* mine = flags.p[rank];
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(flags.p[threadIdx.x] + rank, seq);                     // ready[rank] in rank threadIdx.x's array
+  }
+  if (threadIdx.x < world) {
+    if (!spin_until(mine + threadIdx.x, seq)) atomicExch(error, 1);
+  }
+  __syncthreads();
+
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = (end - begin) >> 2;
+  float* my_params = params.p[rank];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t k = tid; k < n4; k += nth) {
+    const int64_t e = begin + (k << 2);
+    float4 g;
+    if (MULTIMEM) {
+      g = multimem_ld_reduce_add(mc_grads + e);
+    } else {
+      g = zero4;
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q) {
+        if (q < world) {
+          const float4 t = __ldcv(reinterpret_cast<const float4*>(grads.p[q] + e));
+          g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+      }
+    }
+    float4 pp = *reinterpret_cast<const float4*>(my_params + e);
+    float4 mm = *reinterpret_cast<const float4*>(m + e);
+    float4 vv = *reinterpret_cast<const float4*>(v + e);
+    adam_one(pp.x, g.x, mm.x, vv.x, s);
+    adam_one(pp.y, g.y, mm.y, vv.y, s);
+    adam_one(pp.z, g.z, mm.z, vv.z, s);
+    adam_one(pp.w, g.w, mm.w, vv.w, s);
+    *reinterpret_cast<float4*>(m + e) = mm;
+    *reinterpret_cast<float4*>(v + e) = vv;
+    // The parameter stores depend on g, so a warp (in-order issue) reaches the zero stores below only after the
+    // gradient loads have RETURNED: clearing a slice can never overtake the read of that slice.
+    if (MULTIMEM) {
+      multimem_st(mc_params + e, pp);
+      multimem_st(mc_grads + e, zero4);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < world) *reinterpret_cast<float4*>(params.p[q] + e) = pp;
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < world) *reinterpret_cast<float4*>(grads.p[q] + e) = zero4;
+    }
+  }
+  for (int64_t e = begin + (n4 << 2) + tid; e < end; e += nth) {        // ragged tail of the last owner
+    float g = 0.f;
+    for (int q = 0; q < world; ++q) g += __ldcv(grads.p[q] + e);
+    float pp = my_params[e], mm = m[e], vv = v[e];
+    adam_one(pp, g, mm, vv, s);
+    m[e] = mm; v[e] = vv;
+    for (int q = 0; q < world; ++q) params.p[q][e] = pp;
+    for (int q = 0; q < world; ++q) grads.p[q][e] = 0.f;
+  }
+
+  // all of this CTA's peer stores are ordered before its arrival at the counter
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(cta_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) { *cta_counter = 0; __threadfence_system(); }
+    __syncthreads();
+    if (threadIdx.x < world) {
+      st_release_sys(flags.p[threadIdx.x] + kMaxPeers + rank, seq);       // done[rank] in every rank's array
+      if (!spin_until(mine + kMaxPeers + threadIdx.x, seq)) atomicExch(error, 1);
+    }
+  }
+}
+
 }  // namespace mfcd
 
 using namespace mfcd;
+
+extern "C" int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_t* peer_params,
+                                       const uint64_t* peer_flags, uint64_t mc_grads, uint64_t mc_params,
+                                       int32_t rank, int32_t world, int64_t numel, float* m, float* v, float lr,
+                                       float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                                       uint32_t seq, uint32_t* cta_counter, int32_t* error, void* stream) {
+  MFCD_REQUIRE(peer_grads && peer_params && peer_flags && m && v && cta_counter && error,
+               "mfcd_dp_fused_adam_sync: NULL pointer");
+  MFCD_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "mfcd_dp_fused_adam_sync: world must be 1..8");
+  MFCD_REQUIRE(step >= 1 && numel >= 0 && seq >= 1, "mfcd_dp_fused_adam_sync: bad step / numel / seq");
+  PeerTable g, p;
+  FlagTable f;
+  for (int q = 0; q < kMaxPeers; ++q) {
+    g.p[q] = q < world ? reinterpret_cast<float*>(peer_grads[q]) : nullptr;
+    p.p[q] = q < world ? reinterpret_cast<float*>(peer_params[q]) : nullptr;
+    f.p[q] = q < world ? reinterpret_cast<uint32_t*>(peer_flags[q]) : nullptr;
+    if (q < world) {
+      MFCD_REQUIRE(g.p[q] && p.p[q] && f.p[q], "mfcd_dp_fused_adam_sync: NULL peer pointer");
+      MFCD_REQUIRE(((peer_grads[q] | peer_params[q]) & 15u) == 0, "mfcd_dp_fused_adam_sync: peer buffers must be 16-byte aligned");
+    }
+  }
+  int64_t begin = 0, end = 0;
+  int rc = mfcd_dp_shard_range(numel, rank, world, &begin, &end);
+  if (rc != MFCD_OK) return rc;
+  AdamK s;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  s.lr_over_bc1 = (float)((double)lr / bc1);
+  s.bc2_sqrt = (float)sqrt(bc2);
+  s.one_minus_b1 = (float)(1.0 - (double)beta1);
+  s.b2 = beta2;
+  s.one_minus_b2 = (float)(1.0 - (double)beta2);
+  s.eps = eps;
+  s.wd = weight_decay;
+  // every CTA spins at the start, so the whole grid must be co-resident: at most 4 CTAs of 256 threads per SM
+  // (the launch bound keeps the kernel at <= 64 registers).  A rank with an empty slice still takes part in the
+  // flag exchange (one CTA).
+  int grid = grid_for((end - begin + 3) / 4, 256, 4);
+  if (end <= begin) grid = 1;
+  cudaStream_t st = as_stream(stream);
+  if (mc_grads != 0 && mc_params != 0)
+    k_dp_fused_adam_sync<true><<<grid, 256, 0, st>>>(g, p, f, reinterpret_cast<float*>(mc_grads),
+                                                     reinterpret_cast<float*>(mc_params), rank, world, begin, end, m, v,
+                                                     s, seq, cta_counter, error);
+  else
+    k_dp_fused_adam_sync<false><<<grid, 256, 0, st>>>(g, p, f, nullptr, nullptr, rank, world, begin, end, m, v, s, seq,
+                                                      cta_counter, error);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
 
 extern "C" int mfcd_dp_shard_range(int64_t numel, int32_t rank, int32_t world, int64_t* begin, int64_t* end) {
   MFCD_REQUIRE(begin && end && numel >= 0 && world >= 1 && rank >= 0 && rank < world, "mfcd_dp_shard_range: bad argument");

@@ -4,6 +4,15 @@
 #include "common.cuh"
 
 namespace mfcd {
+// records a CUDA event pair around a K1 launch on its stream while mfcd_profile_k1(1) is in effect (bench.py's
+// live roofline measurement of the dominant kernel inside the timed region); free otherwise
+struct K1Timer {
+  explicit K1Timer(cudaStream_t st);
+  ~K1Timer();
+  cudaStream_t st_;
+  bool on_;
+};
+
 int launch_adam(float* p, float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2,
                 float eps, float wd, int64_t step, int zero_grad, cudaStream_t st);
 int launch_sgd(float* p, float* g, float* buf, int64_t numel, float lr, float momentum, float wd,

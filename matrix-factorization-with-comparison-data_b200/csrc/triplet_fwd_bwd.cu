@@ -311,6 +311,7 @@ int launch_fwd_bwd_atomic(const float* U, const float* V, const mfcd_triplet* re
                           const int8_t* item_slot, const int32_t* hot_items, int n_hot, int flags,
                           cudaStream_t st) {
   if (B == 0) return MFCD_OK;
+  K1Timer timer(st);
   HotRows hot{item_slot, hot_items, (item_slot && hot_items) ? n_hot : 0};
   if (hot.n_hot > max_hot_rows(d)) {
     set_error("too many hot rows for d=%d: %d > %d", d, hot.n_hot, max_hot_rows(d));
@@ -593,6 +594,7 @@ int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, 
                        int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
                        float* loss, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (B == 0) return MFCD_OK;
+  K1Timer timer(st);
   if (B <= kSmallB) return launch_det_small(U, V, rec, perm, start, (int)B, d, inv_batch, gU, gV, loss, st);
   const size_t need = det_large_workspace_bytes(B, d);
   if (ws == nullptr || ws_bytes < need) {

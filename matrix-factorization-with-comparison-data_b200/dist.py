@@ -86,9 +86,10 @@ class PartitionedPlan:
 class CudaEngine:
     """K1 / K3 on this rank's GPU through the C ABI."""
 
-    def __init__(self, flat_state, store, perm, spec, mode, use_hot=True):
+    def __init__(self, flat_state, store, perm, spec, mode, use_hot=True, flags=None, hot="auto"):
         self.fs, self.store, self.perm, self.spec, self.mode = flat_state, store, perm, spec, mode
         self.use_hot = use_hot
+        self.flags, self.hot = flags, hot       # overrides: K1 flags of the batch layout, (item_slot, hot_items)
         self.ws = None
 
     def grads(self):
@@ -110,12 +111,17 @@ class CudaEngine:
                                                ws.numel() if ws is not None else 0, current_stream()),
                   "mfcd_triplet_fwd_bwd_det")
         else:
-            hot = self.store.hot_items(fs.m, fs.d, b_local) if self.use_hot else None
+            hot = self.hot
+            if not self.use_hot:
+                hot = None
+            elif isinstance(hot, str):
+                hot = self.store.hot_items(fs.m, fs.d, b_local)
             slot, items, n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
+            flags = self.store.k1_flags(b_local, self.perm) if self.flags is None else int(self.flags)
             check(lib.mfcd_triplet_fwd_bwd_ex(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec),
                                               ptr(self.perm), start, b_local, fs.d, inv, ptr(fs.grads),
                                               ptr(fs.grads[nU:]), ptr(loss_slot), slot, items, n_hot,
-                                              self.store.k1_flags(b_local, self.perm), current_stream()),
+                                              flags, current_stream()),
                   "mfcd_triplet_fwd_bwd_ex")
 
     def update(self, a, b, step):
@@ -137,28 +143,41 @@ class PeerExchange:
     Use:  ex = PeerExchange(numel, dev);  fs = model.flat_state(dev, storage=ex.storage());
           per step: K1 into fs.grads, then ex.step(fs, spec, step)."""
 
-    def __init__(self, numel, device, group=None, use_multimem="auto"):
+    def __init__(self, numel, device, group=None, use_multimem="auto", sync=None):
         import torch.distributed._symmetric_memory as symm_mem
         group = group or dist.group.WORLD
         padded = (numel + 3) // 4 * 4
         self.numel = numel
         self.params = symm_mem.empty(padded, dtype=torch.float32, device=device)
         self.grads = symm_mem.empty(padded, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)      # ready[8] | done[8] (+ padding)
         self.params.zero_()
         self.grads.zero_()
+        self.flags.zero_()
         self.hp = symm_mem.rendezvous(self.params, group)
         self.hg = symm_mem.rendezvous(self.grads, group)
+        self.hf = symm_mem.rendezvous(self.flags, group)
         self.rank, self.world = self.hp.rank, self.hp.world_size
         self.peer_params = (C.c_uint64 * self.world)(*[int(x) for x in self.hp.buffer_ptrs])
         self.peer_grads = (C.c_uint64 * self.world)(*[int(x) for x in self.hg.buffer_ptrs])
+        self.peer_flags = (C.c_uint64 * self.world)(*[int(x) for x in self.hf.buffer_ptrs])
         mc_p = int(getattr(self.hp, "multicast_ptr", 0) or 0)
         mc_g = int(getattr(self.hg, "multicast_ptr", 0) or 0)
         # measured on NVSwitch B200 boxes (profiles/r01_notes.md): in-switch multimem reduction wins at 8 ranks
         # (0.134 vs 0.163 ms per exchange), plain peer loads win at 2 (0.094 vs 0.139 ms); equal at 4.
+        env = os.environ.get("MFCD_DP_MULTIMEM", "auto")
+        if env in ("on", "off"):
+            use_multimem = env == "on"
         if use_multimem == "auto":
             use_multimem = self.world > 4
         self.multimem = bool(use_multimem and mc_p and mc_g)
         self.mc_params, self.mc_grads = (mc_p, mc_g) if self.multimem else (0, 0)
+        # "kernel": flags exchanged inside K9, the owner clears the gradient slices it consumed (default);
+        # "barrier": two symmetric-memory barriers around K9 + a local memset (round-1 path, kept for comparison)
+        self.sync = sync or os.environ.get("MFCD_DP_SYNC", "kernel")
+        self.seq = 0
+        self.cta_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         self.hp.barrier(channel=0)
 
@@ -170,11 +189,25 @@ class PeerExchange:
         check(lib.mfcd_dp_shard_range(self.numel, self.rank, self.world, C.byref(b), C.byref(e)), "mfcd_dp_shard_range")
         return b.value, e.value
 
+    def check_error(self):
+        """one host sync: raises if a bounded in-kernel wait timed out since the last check"""
+        if int(self.error.item()) != 0:
+            self.error.zero_()
+            raise _lib.MfcdError("mfcd_dp_fused_adam_sync: a peer did not arrive in time (results are invalid)")
+
     def step(self, fs, spec, step):
-        """barrier -> K9 (reduce-scatter + Adam + all-gather in one kernel) -> barrier -> clear own gradients"""
+        """K9: reduce-scatter + Adam + all-gather in one kernel; leaves the gradient buffers cleared."""
         if spec.kind != 0:
             raise NotImplementedError("the fused peer exchange implements Adam")
         assert fs.params.data_ptr() == self.params.data_ptr() and fs.grads.data_ptr() == self.grads.data_ptr()
+        if self.sync == "kernel":
+            self.seq += 1
+            check(lib.mfcd_dp_fused_adam_sync(self.peer_grads, self.peer_params, self.peer_flags, self.mc_grads,
+                                              self.mc_params, self.rank, self.world, self.numel, ptr(fs.state1),
+                                              ptr(fs.state2), spec.lr, spec.beta1, spec.beta2, spec.eps,
+                                              spec.weight_decay, step, self.seq, ptr(self.cta_counter),
+                                              ptr(self.error), current_stream()), "mfcd_dp_fused_adam_sync")
+            return
         self.hg.barrier(channel=0)
         check(lib.mfcd_dp_fused_adam(self.peer_grads, self.peer_params, self.mc_grads, self.mc_params, self.rank,
                                      self.world, self.numel, ptr(fs.state1), ptr(fs.state2), spec.lr, spec.beta1,
@@ -233,4 +266,59 @@ def dp_epoch(engine, plan, step0, losses, group=None, bucket_elems=0, exchange=N
             dp_step(engine, plan, k, step0 + k + 1, losses[k:k + 1], group=group, bucket_elems=bucket_elems)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
+    if exchange is not None and exchange.sync == "kernel":
+        exchange.check_error()
     return n_steps
+
+
+class DataParallel:
+    """What train_model drives under world_size > 1: replicated tables (in peer-mapped symmetric memory for the
+    fused K9 exchange), this rank's shard of the triplets, the global batch split evenly over the ranks."""
+
+    def __init__(self, model, device, spec, backend="peer"):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device, self.backend, self.spec = device, backend, spec
+        n, d = model.U.shape
+        m = model.V.shape[0]
+        self.exchange = None
+        if backend == "peer" and spec.kind == 0:
+            self.exchange = PeerExchange((n + m) * d, device)
+            self.fs = model.flat_state(device, storage=self.exchange.storage())
+        else:
+            self.fs = model.flat_state(device)
+        # replicas start bit-identical whatever each rank's host RNG has been through
+        dist.broadcast(self.fs.params, src=0)
+
+    @classmethod
+    def attach(cls, model, device, spec, backend="peer"):
+        dp = getattr(model, "_dp", None)
+        if dp is None or dp.device != device or dp.backend != backend or model._flat is not dp.fs \
+                or (dp.exchange is None) != (backend != "peer" or spec.kind != 0):
+            dp = cls(model, device, spec, backend)
+            model._dp = dp
+        dp.spec = spec
+        return dp
+
+    def train_epoch(self, loader, scatter):
+        """-> per-step GLOBAL batch-mean losses (float32 device tensor), identical on every rank"""
+        fs = self.fs
+        B = loader.batch_size
+        Bl = (B + self.world - 1) // self.world
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        sizes[self.rank] = len(loader.store)
+        dist.all_reduce(sizes)
+        plan = PartitionedPlan(sizes.tolist(), Bl, self.rank)
+        n_steps = plan.n_steps()
+        losses = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=self.device)
+        store, perm, flags, hot = loader.store, None, None, "auto"
+        er = loader.epoch_records(Bl) if (scatter == 0 and Bl > 256) else None
+        if er is not None:
+            store, flags = er
+            hot = loader.store.hot_items(fs.m, fs.d, Bl)
+        else:
+            perm = loader.epoch_perm()
+        engine = CudaEngine(fs, store, perm, self.spec, scatter, flags=flags, hot=hot)
+        with torch.cuda.device(self.device):
+            dp_epoch(engine, plan, fs.step, losses, exchange=self.exchange)
+        fs.step += n_steps
+        return losses[:n_steps]

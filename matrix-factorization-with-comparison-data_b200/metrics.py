@@ -20,31 +20,62 @@ from ._lib import lib, check, ptr, current_stream, MfcdError
 from .store import GroundTruth, compute_device
 
 
-def _row_stats(model, gt: GroundTruth, s: float, engine=None):
+def _row_range(n, world_size):
+    """(rank, world, lo, hi): the rows of X this rank evaluates (all of them on one GPU)"""
+    from .trainer import dist_world
+    from .dist import split_even
+    rank, world = dist_world(world_size)
+    lo, hi = split_even(n, world, rank) if world > 1 else (0, n)
+    return rank, world, lo, hi
+
+
+def _combine_rows(t, world):
+    """rows were computed by their owners into a zero-filled tensor: sum over the ranks = the full tensor"""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def _row_stats(model, gt: GroundTruth, s: float, engine=None, world_size=1):
+    """(n x 8) fp64 row statistics of mfcd_recon_stats as a numpy array, and the model's flat state."""
+    stats, fs = _row_stats_device(model, gt, s, engine=engine, world_size=world_size)
+    return stats.cpu().numpy(), fs
+
+
+def _row_stats_device(model, gt: GroundTruth, s: float, engine=None, world_size=1):
+    """(n x 8) fp64 row statistics of mfcd_recon_stats (device tensor).  Data parallel: each rank streams only
+    its rows of X (K5 shards rows of X), the per-row results are combined with one all-reduce."""
     fs = model.flat_state(gt.device)
     dev = fs.params.device
     n, m, d = fs.n, fs.m, fs.d
     assert gt.shape == (n, m), f"X is {gt.shape}, model is {(n, m)}"
+    rank, world, lo, hi = _row_range(n, world_size)
+    nl = hi - lo
     ubar = torch.empty(d, dtype=torch.float32, device=dev)
     vbar = torch.empty(d, dtype=torch.float32, device=dev)
-    stats = torch.empty((n, 8), dtype=torch.float64, device=dev)
-    xv = gt.xview()
+    stats = torch.zeros((n, 8), dtype=torch.float64, device=dev) if world > 1 else \
+        torch.empty((n, 8), dtype=torch.float64, device=dev)
+    gl = gt.row_slice(lo, hi) if world > 1 else gt
+    xv = gl.xview()
+    Ul = fs.U[lo * d:]
+    sl = stats[lo:]
     with torch.cuda.device(dev):
         st = current_stream()
         check(lib.mfcd_table_col_means(ptr(fs.U), n, d, ptr(ubar), st), "mfcd_table_col_means(U)")
         check(lib.mfcd_table_col_means(ptr(fs.V), m, d, ptr(vbar), st), "mfcd_table_col_means(V)")
         engine = os.environ.get("MFCD_K5", "auto") if engine is None else engine
-        done = False
-        if engine in ("auto", "tc"):
+        done = nl == 0
+        if not done and engine in ("auto", "tc"):
             # tensor-core path (tcgen05 / TMEM) when the shape is eligible; worth it once K = d is big enough
             # for the fp32 FMA pipe to be the limiter of the SIMT engine
             if engine == "tc" or d >= 16:
                 flag = torch.zeros(1, dtype=torch.int32, device=dev)
                 need = C.c_size_t(0)
-                check(lib.mfcd_recon_stats_tc_workspace_bytes(n, m, d, C.byref(need)), "mfcd_recon_stats_tc_workspace_bytes")
+                check(lib.mfcd_recon_stats_tc_workspace_bytes(nl, m, d, C.byref(need)), "mfcd_recon_stats_tc_workspace_bytes")
                 ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
-                rc = lib.mfcd_recon_stats_tc(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar),
-                                             ptr(vbar), ptr(stats), ptr(flag), ptr(ws), need.value, st)
+                rc = lib.mfcd_recon_stats_tc(ptr(Ul), ptr(fs.V), nl, m, d, C.byref(xv), float(s), ptr(ubar),
+                                             ptr(vbar), ptr(sl), ptr(flag), ptr(ws), need.value, st)
                 if rc == 0:
                     if int(flag.item()) == 0:
                         done = True
@@ -57,15 +88,16 @@ def _row_stats(model, gt: GroundTruth, s: float, engine=None):
                 elif rc != -3 or engine == "tc":          # -3 = MFCD_ERR_UNSUPPORTED -> SIMT engine
                     check(rc, "mfcd_recon_stats_tc")
         if not done:
-            check(lib.mfcd_recon_stats(ptr(fs.U), ptr(fs.V), n, m, d, C.byref(xv), float(s), ptr(ubar), ptr(vbar),
-                                       ptr(stats), st), "mfcd_recon_stats")
-    return stats.cpu().numpy(), fs
+            check(lib.mfcd_recon_stats(ptr(Ul), ptr(fs.V), nl, m, d, C.byref(xv), float(s), ptr(ubar), ptr(vbar),
+                                       ptr(sl), st), "mfcd_recon_stats")
+        _combine_rows(stats, world)
+    return stats, fs
 
 
-def compute_reconstruction_error(model, X, s):
+def compute_reconstruction_error(model, X, s, *, world_size=1):
     """|| (UV^T - column means) - sX ||_F / || sX ||_F   (structure.py:939-955)."""
     gt = GroundTruth.wrap(X)
-    st, _ = _row_stats(model, gt, s)
+    st, _ = _row_stats(model, gt, s, world_size=world_size)
     num = math.sqrt(float(st[:, 5].sum()))
     den = abs(float(s)) * math.sqrt(float(st[:, 1].sum()))
     return num / den
@@ -109,13 +141,14 @@ def _svd_error(fs, gt: GroundTruth, alpha, norm_X):
     return float(torch.linalg.norm(diff) / (torch.linalg.norm(S1) + 1e-8))
 
 
-def row_spearman(model, gt: GroundTruth, rows_mask=None, max_bytes=2 << 30):
+def row_spearman(model, gt: GroundTruth, rows_mask=None, max_bytes=2 << 30, world_size=1):
     """Spearman rho of every row of X against the same row of UV^T (float64
-    numpy array of length n; NaN where a row is constant)."""
+    numpy array of length n; NaN where a row is constant).  Data parallel: rows are split over the ranks."""
     fs = model.flat_state(gt.device)
     dev = fs.params.device
     n, m, d = fs.n, fs.m, fs.d
-    rho = torch.empty(n, dtype=torch.float64, device=dev)
+    rank, world, lo, hi = _row_range(n, world_size)
+    rho = torch.zeros(n, dtype=torch.float64, device=dev)
     per_row = 4 * m
     one = C.c_size_t(0)
     check(lib.mfcd_rank_workspace_bytes(1, m, C.byref(one)), "mfcd_rank_workspace_bytes")
@@ -128,24 +161,25 @@ def row_spearman(model, gt: GroundTruth, rows_mask=None, max_bytes=2 << 30):
     rw = torch.empty((chunk, m), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         st = current_stream()
-        for r0 in range(0, n, chunk):
-            nr = min(chunk, n - r0)
+        for r0 in range(lo, hi, chunk):
+            nr = min(chunk, hi - r0)
             xrows = gt.rows(r0, nr).contiguous()
             check(lib.mfcd_reconstruct_rows(ptr(fs.U), ptr(fs.V), r0, nr, m, d, ptr(wrows), st),
                   "mfcd_reconstruct_rows")
             check(lib.mfcd_row_ranks(ptr(xrows), nr, m, ptr(rx), ptr(ws), ws.numel(), st), "mfcd_row_ranks(X)")
             check(lib.mfcd_row_ranks(ptr(wrows), nr, m, ptr(rw), ptr(ws), ws.numel(), st), "mfcd_row_ranks(W)")
             check(lib.mfcd_row_pearson(ptr(rx), ptr(rw), nr, m, ptr(rho[r0:]), st), "mfcd_row_pearson")
+        _combine_rows(rho, world)
     return rho.cpu().numpy()
 
 
-def compute_alpha_and_norm_ratios(model, X_init):
+def compute_alpha_and_norm_ratios(model, X_init, *, world_size=1):
     """The reference's 14-tuple (structure.py:958-1082), same order and types:
     alpha, norm_X, norm_ratio, reconstruction_error_scaled, pearson_mean, pearson_std,
     spearman_mean, spearman_std, svd_error_scaled, slopes, correlations,
     spearman_scores, reconstruction_error_scaled_per_row, alpha_per_row."""
     gt = GroundTruth.wrap(X_init)
-    st, fs = _row_stats(model, gt, 1.0)
+    st, fs = _row_stats(model, gt, 1.0, world_size=world_size)
     n, m = gt.shape
     cxx, cww, cxw = _centered_sums(st, float(m))
 
@@ -173,7 +207,7 @@ def compute_alpha_and_norm_ratios(model, X_init):
 
     spearman_scores = []
     if ok.any():
-        rho = row_spearman(model, gt)
+        rho = row_spearman(model, gt, world_size=world_size)
         spearman_scores = [float(r) for r in rho[ok] if not math.isnan(r)]
     spearman_mean = float(np.mean(spearman_scores)) if spearman_scores else 0.0
     pearson_std = float(np.std(correlations)) if correlations else 0.0

@@ -75,6 +75,12 @@ class GroundTruth:
     def dense(self):
         return self.X if self.X is not None else self.rows(0, self.shape[0])
 
+    def row_slice(self, lo, hi):
+        """Ground truth of users [lo, hi) as a view (no copy): what one data-parallel rank samples from."""
+        if self.X is not None:
+            return GroundTruth(X=self.X[lo:hi], device=self.device)
+        return GroundTruth(A=self.A[lo:hi], B=self.B, scale=self.scale, device=self.device)
+
 
 class TripletStore:
     """N labelled comparisons as 16-byte records {int32 u, i, j; float z} in HBM."""
@@ -185,6 +191,11 @@ class TripletStore:
         self.__dict__.pop("_hot_cache", None)
         return self
 
+    def user_order(self):
+        """int64 CUDA index that sorts the records by user (stable); torch.sort = library call, once per dataset."""
+        with torch.cuda.device(self.device):
+            return torch.sort(self.rec[:, 0], stable=True).indices
+
     def k1_flags(self, batch_size, perm=None):
         """flags for the atomic-mode K1 on batches of `batch_size` walked in store order"""
         grouped = perm is None and getattr(self, "grouped_batch", None) == int(batch_size)
@@ -288,6 +299,74 @@ class TripletLoader:
     def epoch_perm(self):
         return self.begin_iteration()
 
+    # -- throughput batches: shuffle + per-batch user grouping in one pass (csrc/epoch_batches.cu) -----------
+    def _user_sorted(self):
+        """(records sorted by user, index of each sorted record in the original store or None).
+        device RNG: the store order carries no meaning for a shuffled loader, so the store itself is re-ordered
+        (no second copy of a multi-GB shard); reference RNG: epoch permutations index the ORIGINAL order, so a
+        sorted copy is kept next to it."""
+        cached = self.__dict__.get("_sorted")
+        if cached is not None and cached[2] is self.store.rec:
+            return cached[0], cached[1]
+        order = self.store.user_order()
+        with torch.cuda.device(self.store.device):
+            rec = self.store.rec[order].contiguous()
+        if self.shuffle_rng == "reference":
+            out = (rec, order)
+        else:
+            self.store.rec.copy_(rec)
+            self.store.__dict__.pop("_hot_cache", None)
+            self.dataset._data = None
+            out = (self.store.rec, None)
+            del rec
+        self._sorted = (out[0], out[1], self.store.rec)
+        return out
+
+    def epoch_records(self, batch_size=None, seed=None):
+        """This epoch's training records laid out batch after batch, each batch grouped by user:
+        -> (TripletStore, k1 flags), or None when the one-pass multisplit does not apply (more batches per epoch than
+        mfcd_epoch_max_batches; callers then use epoch_perm()).  Consumes the global CPU generator exactly like
+        begin_iteration() (reference RNG) or one seed draw (device RNG)."""
+        B = int(batch_size or self.batch_size)
+        N = len(self.store)
+        if N == 0:
+            return None
+        if not self.shuffle:
+            if self.replay_iter_seed:
+                torch.empty((), dtype=torch.int64).random_()
+            return self.store, self.store.k1_flags(B)
+        cap = C.c_int32(0)
+        check(lib.mfcd_epoch_max_batches(C.byref(cap)), "mfcd_epoch_max_batches")
+        if (N + B - 1) // B > cap.value or N >= (1 << 31):
+            return None
+        dev = self.store.device
+        rec, order = self._user_sorted()
+        pos = None
+        if self.shuffle_rng == "reference":
+            perm = self.begin_iteration()                     # the reference's RandomSampler order
+            with torch.cuda.device(dev):
+                pos0 = torch.empty(N, dtype=torch.int32, device=dev)
+                check(lib.mfcd_invert_perm(ptr(perm), N, ptr(pos0), current_stream()), "mfcd_invert_perm")
+                pos = pos0[order].contiguous()                # position of every record of the SORTED copy
+            seed = 0
+        elif seed is None:
+            if self.replay_iter_seed:
+                torch.empty((), dtype=torch.int64).random_()
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        need = C.c_size_t(0)
+        check(lib.mfcd_epoch_batches_workspace(N, B, C.byref(need)), "mfcd_epoch_batches_workspace")
+        with torch.cuda.device(dev):
+            buf = self.__dict__.get("_epoch_buf")
+            if buf is None or buf.shape[0] != N or buf.device != dev:
+                buf = self._epoch_buf = torch.empty((N, 4), dtype=torch.int32, device=dev)
+            ws = self.__dict__.get("_epoch_ws")
+            if ws is None or ws.numel() < need.value or ws.device != dev:
+                ws = self._epoch_ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
+            check(lib.mfcd_epoch_batches(ptr(rec), N, B, ptr(pos), int(seed), ptr(buf), ptr(ws), ws.numel(),
+                                         current_stream()), "mfcd_epoch_batches")
+        self.last_epoch_seed = int(seed)
+        return TripletStore(buf), _lib.FLAG_USER_GROUPED
+
     def __iter__(self):
         u, i, j, z = self.store.columns()
         perm = self.epoch_perm()
@@ -299,10 +378,76 @@ class TripletLoader:
             yield u[s:e], i[s:e], j[s:e], z[s:e]
 
 
+class HostTripletLoader:
+    """A loader whose records stay in pinned HOST memory and travel to the GPU one batch per optimiser step
+    (datasets that live on the host, or do not fit in HBM).  Stands in for ``DataLoader(dataset, batch_size,
+    shuffle=False)`` (structure.py:739): batches are visited in the order the host laid them out; shuffling a
+    host-resident dataset is the host's job (a reshuffled epoch = a new HostTripletLoader), or upload it once and
+    use TripletLoader.  train_model streams it double-buffered: the copy of batch k+1 overlaps the step on batch k.
+
+    fmt (see include/mfcd_b200.h, hostpack.py):
+      "records16"  (B, 4) int32 records as they sit in HBM                                16 B / triplet
+      "wire8"      uint64 hard-label records, unpacked by mfcd_unpack_triplets8             8 B / triplet
+      "wire_rle"   run-length words of a user-grouped batch, decoded by K1 itself        ~4.5 B / triplet
+    """
+
+    def __init__(self, batches, sizes, fmt="records16", user_grouped=False):
+        assert fmt in ("records16", "wire8", "wire_rle")
+        assert len(batches) == len(sizes)
+        for b in batches:
+            if not (isinstance(b, torch.Tensor) and b.device.type == "cpu" and b.is_pinned() and b.is_contiguous()):
+                raise ValueError("HostTripletLoader needs contiguous PINNED host tensors (torch.Tensor.pin_memory())")
+        self.batches, self.sizes, self.fmt = list(batches), [int(x) for x in sizes], fmt
+        self.user_grouped = bool(user_grouped) or fmt == "wire_rle"
+        self.batch_size = max(self.sizes) if self.sizes else 0
+        self.shuffle = False
+        self.dataset = None
+
+    @classmethod
+    def from_records(cls, rec, batch_size, fmt="records16", user_grouped=False):
+        """rec: (N, 4) int32 records (numpy or CPU tensor), cut into batches of batch_size in order.
+        wire8 / wire_rle are packed here on the host (hostpack.py); wire_rle groups every batch by user first."""
+        import numpy as np
+        from . import hostpack
+        a = rec.numpy() if isinstance(rec, torch.Tensor) else np.asarray(rec)
+        assert a.ndim == 2 and a.shape[1] == 4 and a.dtype == np.int32
+        N, B = a.shape[0], int(batch_size)
+        sizes = [min(B, N - s0) for s0 in range(0, N, B)]
+        if fmt == "records16":
+            host = torch.empty((N, 4), dtype=torch.int32).pin_memory()
+            host.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped)
+        if fmt == "wire8":
+            host = torch.empty(N, dtype=torch.int64).pin_memory()
+            host.copy_(torch.from_numpy(hostpack.pack8(a).view(np.int64)))
+            return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped)
+        words = [hostpack.pack_wire(a[s0:s0 + B] if user_grouped else hostpack.group_by_user(a[s0:s0 + B]))
+                 for s0 in range(0, N, B)]
+        host = torch.empty(sum(len(w) for w in words), dtype=torch.int32).pin_memory()
+        out, o = [], 0
+        for w in words:
+            host[o:o + len(w)].copy_(torch.from_numpy(w.view(np.int32)))
+            out.append(host[o:o + len(w)])
+            o += len(w)
+        return cls(out, sizes, fmt, True)
+
+    def __len__(self):
+        return len(self.batches)
+
+    def n_samples(self):
+        return sum(self.sizes)
+
+    def bytes_per_step(self):
+        return sum(b.numel() * b.element_size() for b in self.batches) / max(len(self.batches), 1)
+
+    def begin_iteration(self):
+        return None
+
+
 def as_loader(loader, device=None) -> TripletLoader:
     """Accept a TripletLoader, or a stock torch DataLoader over (u,i,j,z) rows
     (materialised once into records)."""
-    if isinstance(loader, TripletLoader):
+    if isinstance(loader, (TripletLoader, HostTripletLoader)):
         return loader
     ds = getattr(loader, "dataset", None)
     if ds is None:

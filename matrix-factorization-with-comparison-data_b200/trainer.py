@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr, current_stream
-from .store import GroundTruth, TripletLoader, TripletStore, as_loader, compute_device
+from .store import GroundTruth, HostTripletLoader, TripletLoader, TripletStore, as_loader, compute_device
 
 MODE_ATOMIC = 0
 MODE_DETERMINISTIC = 1
@@ -213,9 +213,12 @@ def _export_optimizer_state(model, optimizer, fs, spec):
             optimizer.state[p] = {"momentum_buffer": fs.state1[sl].view(shape)}
 
 
-def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: OptimizerSpec, mode):
+def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: OptimizerSpec, mode, *, flags=None,
+              hot="auto"):
     """One epoch of structure.py:845-852 through mfcd_train_epoch; returns the
-    per-step batch-mean losses as a float32 device tensor."""
+    per-step batch-mean losses as a float32 device tensor.
+    flags: MFCD_FLAG_* for the atomic K1 (None = what the store knows about its own layout);
+    hot:   (item_slot, hot_items) for hot-row privatisation, None = off, "auto" = counted on `store`."""
     N = len(store)
     n_steps = (N + batch_size - 1) // batch_size
     dev = fs.params.device
@@ -226,7 +229,7 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     a.params, a.grads, a.state1, a.state2 = ptr(fs.params), ptr(fs.grads), ptr(fs.state1), ptr(fs.state2)
     a.n_users, a.n_items, a.d = fs.n, fs.m, fs.d
     a.optimizer, a.mode = spec.kind, mode
-    a.flags = store.k1_flags(batch_size, perm) if mode == MODE_ATOMIC else 0
+    a.flags = (store.k1_flags(batch_size, perm) if flags is None else int(flags)) if mode == MODE_ATOMIC else 0
     a.rec, a.perm = ptr(store.rec), ptr(perm)
     a.n_samples, a.batch_size = N, batch_size
     a.lr, a.beta1, a.beta2, a.eps = spec.lr, spec.beta1, spec.beta2, spec.eps
@@ -237,7 +240,10 @@ def run_epoch(fs: _FlatState, store: TripletStore, perm, batch_size, spec: Optim
     check(lib.mfcd_train_epoch_workspace(C.byref(a), C.byref(ws_bytes)), "mfcd_train_epoch_workspace")
     ws = fs.ensure_workspace(ws_bytes.value)
     a.workspace, a.workspace_bytes = ptr(ws), (ws.numel() if ws is not None else 0)
-    hot = store.hot_items(fs.m, fs.d, batch_size) if mode == MODE_ATOMIC else None
+    if mode != MODE_ATOMIC:
+        hot = None
+    elif isinstance(hot, str):
+        hot = store.hot_items(fs.m, fs.d, batch_size)
     a.item_slot, a.hot_items, a.n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
     with torch.cuda.device(dev):
         a.stream = current_stream()
@@ -262,61 +268,255 @@ def eval_batches(fs: _FlatState, store: TripletStore, batch_size):
 def _sum_like_python(values):
     """`total += loss.item()` over float32 values, in double, in order."""
     tot = 0.0
-    for v in values.tolist():
+    for v in (values if isinstance(values, list) else values.tolist()):
         tot += v
     return tot
 
 
+def dist_world(world_size=None):
+    """(rank, world) of the data-parallel job this process belongs to.  world_size None = what torchrun's
+    environment says (WORLD_SIZE / RANK / LOCAL_RANK); > 1 initialises torch.distributed (NCCL) if needed."""
+    import torch.distributed as dist
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else int(os.environ.get("WORLD_SIZE", "1"))
+    world_size = int(world_size)
+    if world_size <= 1:
+        return 0, 1
+    if not dist.is_initialized():
+        from . import dist as mdist
+        mdist.init_from_env()
+    if not dist.is_initialized() or dist.get_world_size() != world_size:
+        raise ValueError(f"world_size={world_size} needs a torch.distributed job of that size "
+                         f"(launch with torchrun --nproc-per-node {world_size})")
+    return dist.get_rank(), world_size
+
+
+def _all_sum(values, dev, world):
+    """sum of a few python numbers over the ranks (float64)"""
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+class _Stager:
+    """Two device staging slots + a copy stream for a HostTripletLoader (kept on the loader between epochs)."""
+
+    def __init__(self, loader: HostTripletLoader, dev):
+        self.dev = dev
+        B = loader.batch_size
+        self.rec = [torch.empty((B, 4), dtype=torch.int32, device=dev) for _ in range(2)] \
+            if loader.fmt != "wire_rle" else [None, None]
+        self.raw = None
+        if loader.fmt == "wire8":
+            self.raw = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        elif loader.fmt == "wire_rle":
+            cap = max(b.numel() for b in loader.batches)
+            self.raw = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+
+
+def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec, scatter, dp=None, hot=None):
+    """One epoch over a HOST-resident loader: per optimiser step the batch is copied host -> device from pinned
+    memory on a copy stream (double-buffered: the copy of batch k+1 overlaps the step on batch k), K1 runs on the
+    staged batch (wire8: after the unpack kernel; wire_rle: K1 decodes the wire words itself), then the update /
+    exchange, and the step's loss is copied back and READ BY THE HOST every step (one step behind the launches, so
+    the GPU never waits for python).  Returns the per-step losses as a python list."""
+    dev = fs.params.device
+    st = loader.__dict__.get("_stager")
+    if st is None or st.dev != dev:
+        st = loader._stager = _Stager(loader, dev)
+    n_steps = len(loader)
+    world = dp.world if dp is not None else 1
+    sizes = torch.tensor(loader.sizes, dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.all_reduce(sizes)                       # global batch of every step
+    gsizes = sizes.tolist()
+    losses = torch.zeros(max(n_steps, 1), dtype=torch.float32, device=dev)
+    loss_host = torch.zeros(max(n_steps, 1), dtype=torch.float32).pin_memory()
+    nU = fs.n * fs.d
+    direct = loader.fmt == "wire_rle"
+    flags = (_lib.FLAG_USER_GROUPED if loader.user_grouped else 0) | (_lib.FLAG_WIRE_RLE if direct else 0)
+    slot, items, n_hot = (ptr(hot[0]), ptr(hot[1]), hot[1].numel()) if hot else (None, None, 0)
+    out = []
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+
+        def upload(k):
+            b = k % 2
+            with torch.cuda.stream(st.copy_stream):
+                st.copy_stream.wait_event(st.freed[b])
+                h = loader.batches[k]
+                if loader.fmt == "records16":
+                    st.rec[b][: h.shape[0]].copy_(h, non_blocking=True)
+                else:
+                    st.raw[b][: h.numel()].copy_(h, non_blocking=True)
+                    if loader.fmt == "wire8":
+                        check(lib.mfcd_unpack_triplets8(ptr(st.raw[b]), loader.sizes[k], ptr(st.rec[b]),
+                                                        st.copy_stream.cuda_stream), "mfcd_unpack_triplets8")
+                st.ready[b].record(st.copy_stream)
+
+        for b in range(2):
+            st.freed[b].record(main)
+        if n_steps:
+            upload(0)
+        pending = None
+        for k in range(n_steps):
+            if k + 1 < n_steps:
+                upload(k + 1)
+            b = k % 2
+            main.wait_event(st.ready[b])
+            src = st.raw[b] if direct else st.rec[b]
+            Bk = loader.sizes[k]
+            if scatter == MODE_ATOMIC:
+                check(lib.mfcd_triplet_fwd_bwd_ex(ptr(fs.params), ptr(fs.params[nU:]), ptr(src), None, 0, Bk, fs.d,
+                                                  1.0 / float(gsizes[k]), ptr(fs.grads), ptr(fs.grads[nU:]),
+                                                  ptr(losses[k:k + 1]), slot, items, n_hot, flags, main.cuda_stream),
+                      "mfcd_triplet_fwd_bwd_ex")
+            else:
+                if direct:
+                    raise _lib.MfcdError("the wire_rle staging format is decoded by the atomic K1 only")
+                need = C.c_size_t(0)
+                check(lib.mfcd_det_workspace_bytes(Bk, fs.d, C.byref(need)), "mfcd_det_workspace_bytes")
+                ws = fs.ensure_workspace(need.value)
+                check(lib.mfcd_triplet_fwd_bwd_det(ptr(fs.params), ptr(fs.params[nU:]), ptr(src), None, 0, Bk, fs.d,
+                                                   1.0 / float(gsizes[k]), fs.n, fs.m, ptr(fs.grads),
+                                                   ptr(fs.grads[nU:]), ptr(losses[k:k + 1]), ptr(ws),
+                                                   ws.numel() if ws is not None else 0, main.cuda_stream),
+                      "mfcd_triplet_fwd_bwd_det")
+            st.freed[b].record(main)
+            step = fs.step + 1
+            if dp is not None and dp.exchange is not None:
+                dp.exchange.step(fs, spec, step)
+            else:
+                if dp is not None:
+                    import torch.distributed as tdist
+                    tdist.all_reduce(fs.grads)
+                if spec.kind == 0:
+                    check(lib.mfcd_adam_update(ptr(fs.params), ptr(fs.grads), ptr(fs.state1), ptr(fs.state2),
+                                               fs.params.numel(), spec.lr, spec.beta1, spec.beta2, spec.eps,
+                                               spec.weight_decay, step, 1, main.cuda_stream), "mfcd_adam_update")
+                else:
+                    check(lib.mfcd_sgd_update(ptr(fs.params), ptr(fs.grads), ptr(fs.state1), fs.params.numel(), spec.lr,
+                                              spec.momentum, spec.weight_decay, step, 1, main.cuda_stream),
+                          "mfcd_sgd_update")
+            fs.step = step
+            # the step's result goes back to the host every step; it is read once the NEXT step is queued
+            loss_host[k:k + 1].copy_(losses[k:k + 1], non_blocking=True)
+            st.done[b].record(main)
+            if pending is not None:
+                st.done[pending % 2].synchronize()
+                out.append(float(loss_host[pending]))
+            pending = k
+        if pending is not None:
+            st.done[pending % 2].synchronize()
+            out.append(float(loss_host[pending]))
+    if world > 1:       # local partial sums (each scaled by 1 / global batch) -> global batch means
+        t = torch.tensor(out, dtype=torch.float64, device=dev)
+        import torch.distributed as tdist
+        tdist.all_reduce(t)
+        out = t.tolist()
+        if dp.exchange is not None and dp.exchange.sync == "kernel":
+            dp.exchange.check_error()
+    return out
+
+
+def train_epoch(fs: _FlatState, train_loader: TripletLoader, spec: OptimizerSpec, scatter, dp=None):
+    """One training epoch through the product path: the epoch's reshuffle, then every optimiser step
+    (K1 -> [gradient exchange] -> K3), no host sync.  Returns the per-step batch-mean losses (float32, device).
+
+    Throughput batches (atomic scatter, more than 256 triplets): the reshuffle is the one-pass multisplit of
+    csrc/epoch_batches.cu -- same batches as walking a random permutation in chunks of B, each batch laid out
+    grouped by user -- so K1 runs with user runs and hot-row privatisation.  Reference-sized or deterministic
+    batches: the epoch permutation is handed to the kernels as is (batch order = the reference's summation order).
+    dp: a dist.DataParallel (replicated tables, this rank's shard in `train_loader`)."""
+    if isinstance(train_loader, HostTripletLoader):
+        return stream_epoch(fs, train_loader, spec, scatter, dp=dp, hot=train_loader.__dict__.get("hot"))
+    if dp is not None:
+        return dp.train_epoch(train_loader, scatter)
+    B = train_loader.batch_size
+    if scatter == MODE_ATOMIC and B > 256:
+        er = train_loader.epoch_records(B)
+        if er is not None:
+            ep_store, flags = er
+            hot = train_loader.store.hot_items(fs.m, fs.d, B)
+            return run_epoch(fs, ep_store, None, B, spec, scatter, flags=flags, hot=hot)
+    perm = train_loader.epoch_perm()
+    return run_epoch(fs, train_loader.store, perm, B, spec, scatter)
+
+
 def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=100, is_last=False,
-                open_browser=False, *, mode="auto", progress=False):
+                open_browser=False, *, mode="auto", progress=False, world_size=None, dp_backend="peer"):
     """Same contract as the reference's train_model (structure.py:812-878):
     returns ``(train_losses, val_losses)``, one mean-of-batch-means per epoch.
 
-    Per epoch the whole batch loop runs inside one C call (K1 + K3 per step, no
-    per-step host sync; the reference syncs on ``loss.item()`` every step)."""
+    Per epoch the whole batch loop runs without a host sync (the reference syncs on ``loss.item()`` every step).
+    Keyword-only extras (reference behaviour by default): ``mode`` = scatter mode ('auto': deterministic up to
+    256 triplets per batch, atomic above); ``world_size`` > 1 (or a torchrun environment) = data-parallel training,
+    every rank passing ITS shard of the triplets and ``train_loader.batch_size`` meaning the GLOBAL batch."""
     dev = compute_device(device)
     train_loader = as_loader(train_loader, dev)
     val_loader = as_loader(val_loader, dev)
-    fs = model.flat_state(dev)
     spec = OptimizerSpec(optimizer)
+    rank, world = dist_world(world_size)
+    dp = None
+    if world > 1:
+        from . import dist as mdist
+        dp = mdist.DataParallel.attach(model, dev, spec, backend=dp_backend)
+        fs = dp.fs
+    else:
+        fs = model.flat_state(dev)
     _import_optimizer_state(model, optimizer, fs)
     scatter = resolve_mode(mode, train_loader.batch_size)
 
     train_losses, val_losses = [], []
     epochs = range(num_epochs)
-    if progress:
+    if progress and rank == 0:
         from tqdm import tqdm
         epochs = tqdm(epochs, desc="Training Progress")
     for _ in epochs:
-        perm = train_loader.epoch_perm()
-        step_losses = run_epoch(fs, train_loader.store, perm, train_loader.batch_size, spec, scatter)
+        step_losses = train_epoch(fs, train_loader, spec, scatter, dp=dp)
         val_loader.begin_iteration()
         vloss, _ = eval_batches(fs, val_loader.store, val_loader.batch_size)
         # one host sync per epoch
-        train_losses.append(_sum_like_python(step_losses) / len(train_loader))
-        val_losses.append(_sum_like_python(vloss) / len(val_loader))      # ZeroDivisionError like the reference
+        if world > 1:       # step_losses already holds the GLOBAL batch means (all-reduced once per epoch)
+            train_losses.append(_sum_like_python(step_losses) / len(step_losses))
+            vsum, vcnt = _all_sum([_sum_like_python(vloss), len(val_loader)], dev, world)
+        else:
+            train_losses.append(_sum_like_python(step_losses) / len(train_loader))
+            vsum, vcnt = _sum_like_python(vloss), len(val_loader)
+        val_losses.append(vsum / vcnt)                                    # ZeroDivisionError like the reference
     _export_optimizer_state(model, optimizer, fs, spec)
     if device is not None and torch.device(device).type == "cpu":
         model.mirror_to_host()
     return train_losses, val_losses
 
 
-def evaluate_model(model, test_loader, device):
-    """(mean-of-batch-means BCE, accuracy) on the test loader (structure.py:881-921)."""
+def evaluate_model(model, test_loader, device, *, world_size=None):
+    """(mean-of-batch-means BCE, accuracy) on the test loader (structure.py:881-921).  Data parallel: every
+    rank passes its shard; sums are combined over the ranks."""
     dev = compute_device(device)
     loader = as_loader(test_loader, dev)
     fs = model.flat_state(dev)
+    rank, world = dist_world(world_size)
     loader.begin_iteration()
     batch_loss, correct = eval_batches(fs, loader.store, loader.batch_size)
-    total = len(loader.store)
-    accuracy = int(correct.item()) / total if total > 0 else 0.0
-    return _sum_like_python(batch_loss) / len(loader), accuracy
+    lsum, nb, ncorrect, total = _all_sum([_sum_like_python(batch_loss), len(loader), int(correct.item()),
+                                          len(loader.store)], dev, world)
+    accuracy = ncorrect / total if total > 0 else 0.0
+    return lsum / nb, accuracy
 
 
-def compute_ground_truth_metrics(test_loader, X, device):
+def compute_ground_truth_metrics(test_loader, X, device, *, world_size=None):
     """(mean-of-batch-means MSE of sigmoid(X[u,i]-X[u,j]) vs label, accuracy of
     (diff > 0) == label) -- structure.py:1085-1127; note: no scale s."""
     dev = compute_device(device)
+    rank, world = dist_world(world_size)
     loader = as_loader(test_loader, dev)
     gt = GroundTruth.wrap(X, dev)
     loader.begin_iteration()
@@ -328,5 +528,6 @@ def compute_ground_truth_metrics(test_loader, X, device):
     with torch.cuda.device(dev):
         check(lib.mfcd_ground_truth_eval(C.byref(xv), ptr(loader.store.rec), N, loader.batch_size, ptr(batch_mse),
                                          ptr(correct), current_stream()), "mfcd_ground_truth_eval")
-    accuracy = int(correct.item()) / N if N > 0 else 0.0
-    return _sum_like_python(batch_mse[:nb]) / nb, accuracy
+    msum, nbs, ncorrect, total = _all_sum([_sum_like_python(batch_mse[:nb]), nb, int(correct.item()), N], dev, world)
+    accuracy = ncorrect / total if total > 0 else 0.0
+    return msum / nbs, accuracy

@@ -32,6 +32,7 @@ from mfcd_b200 import config as _cfg
 from mfcd_b200 import metrics as _metrics
 from mfcd_b200 import sampling as _sampling
 from mfcd_b200 import trainer as _trainer
+from mfcd_b200 import dist as _mdist
 from mfcd_b200.store import GroundTruth, TripletLoader, TripletStore, compute_device
 from mfcd_b200.trainer import MatrixFactorization  # noqa: F401  (structure.py:746)
 from generation_data import *  # noqa: F401,F403  (the reference re-exports it, structure.py:17)
@@ -87,7 +88,8 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
                    lr=1e-3, weight_decay=1e-5, num_epochs=30, reps=1, strategy="random",
                    open_browser=False, linear=False, K=1, d1=None,
                    save_path=None, save_every=None, popularity_method="zipf",
-                   alpha=1.5, soft_label=False, generation="base"):
+                   alpha=1.5, soft_label=False, generation="base", *,
+                   batch_size=64, mode=None, world_size=None, concurrency=None):
     """Grid (default) or synchronised linear sweep over scalar-or-list arguments;
     one ``run_experiment`` per configuration.  Returns ``[{'params', 'results'}]``
     -- or ``[]`` when ``save_path`` is set, because saved chunks are dropped from
@@ -117,7 +119,7 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
             weight_decay=cfg['weight_decay'], reps=cfg['reps'], num_epochs=cfg['num_epochs'],
             open_browser=open_browser, K=cfg['K'], d1=cfg['d1'], strategy=cfg['strategy'],
             popularity_method=cfg['popularity_method'], alpha=cfg['alpha'], soft_label=cfg['soft_label'],
-            generation=cfg['generation'])
+            generation=cfg['generation'], batch_size=batch_size, mode=mode, world_size=world_size)
         pending.append({'params': cfg, 'results': results})
         if save_path and save_every and len(pending) >= save_every:
             _append_pickle(save_path, pending)
@@ -143,6 +145,14 @@ def print_return_structure_types(obj, prefix="root"):
         print(f"{prefix}: {type(obj).__name__}")
 
 
+def _common_seed():
+    """one 62-bit seed, the same on every rank of the data-parallel job (rank 0's draw)"""
+    import torch.distributed as dist
+    seed = torch.tensor([_sampling.fresh_seed()], dtype=torch.int64, device=compute_device(None))
+    dist.broadcast(seed, src=0)
+    return int(seed.item()) % (2 ** 62)
+
+
 _RESULT_KEYS = (
     "reconstruction_errors", "log_likelihoods", "accuracy", "gt_log_likelihoods", "gt_accuracy",
     "train_losses", "val_losses", "alpha", "norm_X", "norm_ratio", "reconstruction_error_scaled",
@@ -153,33 +163,46 @@ _RESULT_KEYS = (
 
 def run_experiment(n, m, d, p, s, device, lr, weight_decay, reps=5, num_epochs=100, open_browser=False, K=1,
                    d1=None, strategy="random", popularity_method="zipf", alpha=1.5, soft_label=False,
-                   generation="base"):
+                   generation="base", *, batch_size=64, mode=None, world_size=None):
     """``reps`` independent repetitions of: ground truth -> triplets + BTL labels ->
     train -> evaluate; returns the reference's 23-key dict of per-repetition lists
-    (structure.py:420-444)."""
+    (structure.py:420-444).
+
+    Keyword-only extras, reference behaviour by default: ``batch_size`` (the reference
+    hard-wires 64, structure.py:668), ``mode`` (scatter mode, None = mfcd_b200.config.SCATTER_MODE), ``world_size``
+    (None = torchrun's environment; > 1 = data-parallel: every rank samples and labels the triplets of its own
+    user range, the tables are replicated, metrics are combined over the ranks; every rank returns the same dict)."""
+    rank, world = _trainer.dist_world(world_size)
     out = {key: [] for key in _RESULT_KEYS}
     for rep in range(reps):
         if d1 is None:
             d1 = d
+        if world > 1:
+            base = _common_seed()
+            torch.manual_seed(base)                      # the same ground truth on every rank
         X = generate_X(n, m, d, device, generation=generation)
         num_triplets = int(n * m * p / 2)
+        if world > 1:
+            torch.manual_seed(base + 1000003 * (rank + 1))   # per-rank sampling / label streams
         train_loader, val_loader, test_loader = split_dataset_from_triplets(
-            X, num_triplets, scale=s, K=K, strategy=strategy,
-            popularity_method=popularity_method, alpha=alpha, soft_label=soft_label)
+            X, num_triplets, scale=s, K=K, batch_size=batch_size, strategy=strategy,
+            popularity_method=popularity_method, alpha=alpha, soft_label=soft_label, world_size=world)
+        if world > 1:
+            torch.manual_seed(base + 1)                  # common stream again: model init, sampled rows
 
         model = MatrixFactorization(n, m, d).to(device)
         optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
         t_losses, v_losses = train_model(model, train_loader, val_loader, optimizer, device,
                                          num_epochs=num_epochs, is_last=(rep == reps - 1),
-                                         open_browser=open_browser)
-        test_loss, test_acc = evaluate_model(model, test_loader, device)
-        rec_error = compute_reconstruction_error(model, X, s)
+                                         open_browser=open_browser, mode=mode, world_size=world)
+        test_loss, test_acc = evaluate_model(model, test_loader, device, world_size=world)
+        rec_error = compute_reconstruction_error(model, X, s, world_size=world)
         (alpha_val, norm_X_val, norm_ratio_val, rec_scaled, pearson_mean, pearson_std, spearman_mean,
          spearman_std, svd_err, slopes, correlations, spearman_scores, rec_scaled_per_row,
-         alpha_per_row) = compute_alpha_and_norm_ratios(model, X)
+         alpha_per_row) = compute_alpha_and_norm_ratios(model, X, world_size=world)
         rand_indices = torch.randperm(X.shape[0])[:2]                     # structure.py:390
         sampled_X_rows, sampled_UVT_rows = _metrics.sampled_rows(model, X, rand_indices.tolist())
-        gt_loss, gt_acc = compute_ground_truth_metrics(test_loader, X, device)
+        gt_loss, gt_acc = compute_ground_truth_metrics(test_loader, X, device, world_size=world)
 
         for key, value in (
                 ("reconstruction_errors", rec_error), ("log_likelihoods", -test_loss), ("accuracy", test_acc),
@@ -329,10 +352,26 @@ def _split_permutation(total, device):
 def split_dataset_from_triplets(X, num_triplets, scale=1.0, K=1,
                                 train_ratio=0.8, val_ratio=0.1,
                                 batch_size=64, strategy="random",
-                                popularity_method="zipf", alpha=1.5, soft_label=False):
+                                popularity_method="zipf", alpha=1.5, soft_label=False, *, world_size=1):
     """Sample triplets, split 80/10/10 with the fixed seed 42, top the test split
     up to >= 500 points, label the three splits and wrap them in loaders
-    (structure.py:666-742).  Returns (train_loader, val_loader, test_loader)."""
+    (structure.py:666-742).  Returns (train_loader, val_loader, test_loader).
+
+    world_size > 1 (data parallel): this rank runs the same pipeline on ITS slice of the
+    users -- rows [lo, hi) of X, num_triplets / world of the triplets -- so the ranks hold disjoint shards (a
+    triplet's key contains its user) and no cross-rank dedup is needed.  ``batch_size`` stays the GLOBAL batch."""
+    rank, world = _trainer.dist_world(world_size)
+    if world > 1:
+        lo, hi = _mdist.split_even(X.shape[0], world, rank)
+        a, b = _mdist.split_even(num_triplets, world, rank)
+        Xs = X.row_slice(lo, hi) if isinstance(X, GroundTruth) else X[lo:hi]
+        loaders = split_dataset_from_triplets(Xs, b - a, scale=scale, K=K, train_ratio=train_ratio,
+                                              val_ratio=val_ratio, batch_size=batch_size, strategy=strategy,
+                                              popularity_method=popularity_method, alpha=alpha,
+                                              soft_label=soft_label, world_size=1)
+        for ld in loaders:
+            ld.store.rec[:, 0] += lo                      # local user ids -> global
+        return loaders
     n, m = X.shape
     found = get_triplets_from_X(X, num_triplets, strategy=strategy, popularity_method=popularity_method,
                                 alpha=alpha)
@@ -384,30 +423,35 @@ def split_dataset_from_triplets(X, num_triplets, scale=1.0, K=1,
 # training / evaluation (hot path)
 # ---------------------------------------------------------------------------
 def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=100, is_last=False,
-                open_browser=False):
-    """Per-epoch mean-of-batch-means training and validation BCE (structure.py:812-878)."""
+                open_browser=False, *, mode=None, world_size=None):
+    """Per-epoch mean-of-batch-means training and validation BCE (structure.py:812-878).
+    Keyword-only extras: ``mode`` (scatter mode; None = mfcd_b200.config.SCATTER_MODE, 'auto' = deterministic for
+    batches up to 256, atomic above) and ``world_size`` (data parallel; None = torchrun's environment).  The batch
+    size is the loader's (``split_dataset_from_triplets(..., batch_size=...)``)."""
     return _trainer.train_model(model, train_loader, val_loader, optimizer, device, num_epochs=num_epochs,
-                                is_last=is_last, open_browser=open_browser, mode=_cfg.SCATTER_MODE, progress=True)
+                                is_last=is_last, open_browser=open_browser,
+                                mode=_cfg.SCATTER_MODE if mode is None else mode, progress=True,
+                                world_size=world_size)
 
 
-def evaluate_model(model, test_loader, device):
+def evaluate_model(model, test_loader, device, *, world_size=None):
     """(test BCE as mean of batch means, accuracy)  (structure.py:881-921)."""
-    return _trainer.evaluate_model(model, test_loader, device)
+    return _trainer.evaluate_model(model, test_loader, device, world_size=world_size)
 
 
-def compute_reconstruction_error(model, X, s):
+def compute_reconstruction_error(model, X, s, *, world_size=None):
     """|| (UV^T - column means) - sX ||_F / || sX ||_F  (structure.py:925-955)."""
-    return _metrics.compute_reconstruction_error(model, X, s)
+    return _metrics.compute_reconstruction_error(model, X, s, world_size=world_size)
 
 
-def compute_alpha_and_norm_ratios(model, X_init):
+def compute_alpha_and_norm_ratios(model, X_init, *, world_size=None):
     """14 alignment metrics between row-centred UV^T and X (structure.py:958-1082)."""
-    return _metrics.compute_alpha_and_norm_ratios(model, X_init)
+    return _metrics.compute_alpha_and_norm_ratios(model, X_init, world_size=world_size)
 
 
-def compute_ground_truth_metrics(test_loader, X, device):
+def compute_ground_truth_metrics(test_loader, X, device, *, world_size=None):
     """(MSE of sigmoid(X[u,i]-X[u,j]) vs labels, accuracy of the sign)  (structure.py:1085-1127)."""
-    return _trainer.compute_ground_truth_metrics(test_loader, X, device)
+    return _trainer.compute_ground_truth_metrics(test_loader, X, device, world_size=world_size)
 
 
 def start_tensorboard(log_dir='runs/matrix_factorization', port=6006, open_browser=True):

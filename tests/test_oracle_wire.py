@@ -39,3 +39,28 @@ def test_round_trip(N, n):
     assert len(w) == 4 + 3 * ((N + 31) // 32) + N + len(np.unique(u))
     uu, ii, jj, zz = W.unpack_wire(w)
     assert (uu == u).all() and (ii == i).all() and (jj == j).all() and (zz == z).all()
+
+
+@pytest.mark.parametrize("N,n", [(1, 5), (33, 2), (8193, 5000)])
+def test_product_host_packers_match_the_oracle(N, n):
+    """mfcd_b200.hostpack (the numpy packers a host-side loader uses) == the independent restatement above."""
+    from mfcd_b200 import hostpack
+    rng = np.random.default_rng(N + 1)
+    u = np.sort(rng.integers(0, n, N))
+    i, j = rng.integers(0, 65536, N), rng.integers(0, 65536, N)
+    z = rng.integers(0, 2, N).astype(np.float64)
+    rec = hostpack.as_records(u, i, j, z)
+    assert np.array_equal(hostpack.pack_wire(rec), W.pack_wire(u, i, j, z))
+    p8 = hostpack.pack8(rec)
+    assert np.array_equal(p8 >> np.uint64(41), u.astype(np.uint64))
+    assert np.array_equal((p8 >> np.uint64(21)) & np.uint64(0xFFFFF), i.astype(np.uint64))
+    assert np.array_equal((p8 >> np.uint64(1)) & np.uint64(0xFFFFF), j.astype(np.uint64))
+    assert np.array_equal(p8 & np.uint64(1), z.astype(np.uint64))
+    shuffled = rec[rng.permutation(N)]
+    g = hostpack.group_by_user(shuffled)
+    assert (np.diff(g[:, 0]) >= 0).all() and sorted(map(tuple, g)) == sorted(map(tuple, shuffled))
+    soft = rec.copy(); soft[0, 3] = np.float32(0.5).view(np.int32)
+    with pytest.raises(ValueError):
+        hostpack.pack_wire(soft)
+    with pytest.raises(ValueError):
+        hostpack.pack8(soft)
