@@ -108,8 +108,9 @@ def main():
     report["eval_loss_rel"] = rel(loss, ol)
     report["eval_acc_abs"] = abs(acc - oa)
     fs = model.flat_state(dev)
-    gathered = [torch.zeros_like(fs.params) for _ in range(world)]
-    dist.all_gather(gathered, fs.params.contiguous())
+    mine_p = fs.params.detach().cpu().contiguous() if KIND == "gloo1" else fs.params.contiguous()
+    gathered = [torch.zeros_like(mine_p) for _ in range(world)]
+    dist.all_gather(gathered, mine_p)
     report["replicas_identical"] = all(torch.equal(gathered[0], t) for t in gathered)
 
     # ---- 2. atomic, throughput batch, per-epoch device reshuffle + grouping ------------------------------
@@ -146,8 +147,9 @@ def main():
     report["atomic_U_rel"] = rel(model2.U.detach().cpu().numpy(), Uo)
     report["atomic_V_rel"] = rel(model2.V.detach().cpu().numpy(), Vo)
     fs2 = model2.flat_state(dev)
-    gathered = [torch.zeros_like(fs2.params) for _ in range(world)]
-    dist.all_gather(gathered, fs2.params.contiguous())
+    mine_p = fs2.params.detach().cpu().contiguous() if KIND == "gloo1" else fs2.params.contiguous()
+    gathered = [torch.zeros_like(mine_p) for _ in range(world)]
+    dist.all_gather(gathered, mine_p)
     report["atomic_replicas_identical"] = all(torch.equal(gathered[0], t) for t in gathered)
     report["grads_left_clean"] = bool((fs2.grads == 0).all().item())
 
