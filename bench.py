@@ -377,7 +377,7 @@ def main():
                     "last_loss": float(ls[-1])}
 
         formats = ["records16", "wire8"]
-        if m <= 65536 and mode == 0 and d % 4 == 0 and d in (4, 8, 16, 32, 64, 128, 256, 384, 512) and B * K <= (1 << 26):
+        if m <= 65536 and mode == 0 and d % 4 == 0 and d in (4, 8, 16, 32, 64, 128, 256, 384, 512) and B * K <= (1 << 27):
             formats.append("wire_rle")
         for fmt in (formats if args.e2e_format == "all" else [args.e2e_format]):
             e2e_formats[fmt] = run_format(fmt)
@@ -423,20 +423,33 @@ def main():
                           "bound": "hbm", "achieved": 32 * nb / (batching_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": 32 * nb / (batching_ms * 1e-3) / 1e9 / peak, "ms": batching_ms, "bytes_per_launch": 32 * nb,
                           "share_of_epoch": batching_ms / ms})
-        # K5: reconstruction statistics on a dense X of 8192 x 20480 (671 MB), d of this config
+        # K5: reconstruction statistics (tcgen05 / TMEM / TMA engine) on a dense X of 8192 x 20480 (671 MB), through
+        # the C ABI call metrics.py makes, K = d of this config and K = 128
         try:
-            from mfcd_b200 import metrics
             xn, xm = 8192, 20480
-            km = MatrixFactorization(xn, xm, d)
             X = torch.randn(xn, xm, device=dev)
             g5 = GroundTruth(X=X, device=dev)
-            metrics._row_stats(km, g5, 1.0)
-            t_k5 = timed(lambda: metrics._row_stats_device(km, g5, 1.0), reps=5)
-            extra.append({"kernel": "K5 reconstruction statistics (tcgen05/TMA engine where eligible)", "bound": "hbm",
-                          "achieved": 4 * xn * xm / (t_k5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": 4 * xn * xm / (t_k5 * 1e-3) / 1e9 / peak, "ms": t_k5, "bytes_per_launch": 4 * xn * xm,
-                          "shape": [xn, xm, d]})
-            del X, g5, km
+            xv = g5.xview()
+            for dk in sorted({d, 128}):
+                km = MatrixFactorization(xn, xm, dk)
+                kfs = km.flat_state(dev)
+                ubar = torch.zeros(dk, device=dev); vbar = torch.zeros(dk, device=dev)
+                stats = torch.empty((xn, 8), dtype=torch.float64, device=dev)
+                flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                need = C.c_size_t(0)
+                check(lib.mfcd_recon_stats_tc_workspace_bytes(xn, xm, dk, C.byref(need)), "ws")
+                ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
+                run5 = lambda: check(lib.mfcd_recon_stats_tc(ptr(kfs.U), ptr(kfs.V), xn, xm, dk, C.byref(xv), 1.0, ptr(ubar),
+                                                             ptr(vbar), ptr(stats), ptr(flag), ptr(ws), need.value,
+                                                             current_stream()), "k5")
+                t_k5 = timed(run5, reps=10)
+                extra.append({"kernel": f"k_recon_stats_tc (K5, tcgen05 + TMEM + TMA; K = {dk})", "bound": "hbm",
+                              "achieved": 4 * xn * xm / (t_k5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": 4 * xn * xm / (t_k5 * 1e-3) / 1e9 / peak, "ms": t_k5, "bytes_per_launch": 4 * xn * xm,
+                              "shape": [xn, xm, dk], "pipeline_timeout_flag": int(flag.item()),
+                              "tflops_tf32x3": 3 * 2.0 * xn * xm * ((dk + 7) // 8 * 8) / (t_k5 * 1e-3) / 1e12})
+                del km, kfs, ws, stats
+            del X, g5
         except Exception as ex:       # a secondary line must not take the headline down
             extra.append({"kernel": "K5", "error": str(ex)[:200]})
 

@@ -7,8 +7,8 @@
 // batch by user (what K1's user-run path wants), this file does a stable multisplit:
 //
 //   * record r of the store has epoch position pos(r): pos[r] from memory (the inverse of a given
-//     permutation -- reference RNG mode), or a keyed bijection of [0, N) evaluated on the fly (an
-//     alternating unbalanced Feistel network over ceil(log2 N) bits with cycle walking; device RNG mode);
+//     permutation -- reference RNG mode), or a keyed bijection of [0, N) evaluated on the fly (multiply /
+//     xor-shift / add rounds over ceil(log2 N) bits with cycle walking; device RNG mode);
 //   * batch(r) = pos(r) / B -- exactly the batches a loader walking the permutation in chunks of B forms,
 //     every batch has B members (the last one N - (nb-1) B);
 //   * out[] receives batch after batch, each batch's records in STORE order.  When the store is sorted by
@@ -28,53 +28,59 @@ constexpr int kEpochMaxBatches = 1024;     // counters per warp in shared memory
 constexpr int kEpochBlock = 256;
 constexpr int kEpochWarps = kEpochBlock / 32;
 
-struct FeistelKey {
-  uint32_t k[8];
-  uint32_t bits_lo, bits_hi;   // widths of the two halves, bits_lo + bits_hi = ceil(log2 N) (>= 2)
+// Keyed bijection of the bits-wide integers: 4 rounds of  x = x * odd (mod 2^bits);  x ^= x >> bits/2;
+// x = x + key (mod 2^bits)  -- each step is invertible, so the composition is a permutation of [0, 2^bits).
+// Multiplication carries information upward, the xor-shift brings the well-mixed top half back down; the batch of
+// a record is pos / B, i.e. it is decided by the best-mixed (high) bits.  ~20 integer instructions per pass, which
+// matters: the first version of this file used an 8-round Feistel network (~100 instructions per pass, ~4.5 passes
+// per warp with cycle walking) and BOTH kernels were ALU-bound (profiles/r02_notes.md: k_epoch_count 68 % issue
+// active, 0 % DRAM; 3.3 ms per epoch of 84 M records against ~0.6 ms of pure data movement).
+struct ShuffleKey {
+  uint32_t x0, mul[4], add[4];
+  uint32_t bits;      // ceil(log2 N), at least 2, at most 31
 };
 
-__host__ __device__ __forceinline__ uint32_t feistel_f(uint32_t v, uint32_t key) {
-  uint32_t h = v * 0x9E3779B1u + key;
-  h ^= h >> 15; h *= 0x85EBCA77u;
-  h ^= h >> 13; h *= 0xC2B2AE3Du;
-  h ^= h >> 16;
-  return h;
-}
-
-// one pass of the 8-round network on a (bits_lo + bits_hi)-bit value: each round XORs one half with a keyed
-// hash of the other, so every round -- and the whole network -- is a bijection whatever the two widths are
-__host__ __device__ __forceinline__ uint32_t feistel_once(uint32_t x, const FeistelKey& K) {
-  const uint32_t mlo = (1u << K.bits_lo) - 1u, mhi = (1u << K.bits_hi) - 1u;
-  uint32_t lo = x & mlo, hi = x >> K.bits_lo;
+__host__ __device__ __forceinline__ uint32_t shuffle_once(uint32_t x, const ShuffleKey& K) {
+  const uint32_t mask = (1u << K.bits) - 1u;
+  const uint32_t sh = K.bits >> 1;                     // >= 1
+  x ^= K.x0 & mask;
 #pragma unroll
-  for (int r = 0; r < 8; r += 2) {
-    hi ^= feistel_f(lo, K.k[r]) & mhi;
-    lo ^= feistel_f(hi, K.k[r + 1]) & mlo;
+  for (int r = 0; r < 4; ++r) {
+    x = (x * K.mul[r]) & mask;
+    x ^= x >> sh;
+    x = (x + K.add[r]) & mask;
   }
-  return (hi << K.bits_lo) | lo;
-}
-
-// bijection of [0, N): walk the cycle of the 2^bits permutation until it re-enters [0, N)
-__host__ __device__ __forceinline__ uint32_t epoch_position(uint32_t r, uint32_t N, const FeistelKey& K) {
-  uint32_t x = feistel_once(r, K);
-  while (x >= N) x = feistel_once(x, K);
   return x;
 }
 
-static FeistelKey make_key(int64_t N, uint64_t seed) {
-  FeistelKey K;
+// bijection of [0, N): walk the cycle of the 2^bits permutation until it re-enters [0, N)  (N > 2^(bits-1), so
+// a pass lands inside with probability > 1/2)
+__host__ __device__ __forceinline__ uint32_t epoch_position(uint32_t r, uint32_t N, const ShuffleKey& K) {
+  uint32_t x = shuffle_once(r, K);
+  while (x >= N) x = shuffle_once(x, K);
+  return x;
+}
+
+static ShuffleKey make_key(int64_t N, uint64_t seed) {
+  ShuffleKey K;
   int bits = 2;
   while ((int64_t(1) << bits) < N) ++bits;
-  K.bits_lo = bits / 2;
-  K.bits_hi = bits - bits / 2;
+  K.bits = (uint32_t)bits;
+  static const uint32_t M[4] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu};
+  uint32_t k[9];
   uint64_t s = seed;
-  for (int r = 0; r < 8; ++r) {          // splitmix64 stream -> round keys
+  for (int r = 0; r < 9; ++r) {          // splitmix64 stream -> 9 key words (bits 16..47 of each output)
     s += 0x9E3779B97F4A7C15ull;
     uint64_t z = s;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    K.k[r] = (uint32_t)(z >> 16);
+    k[r] = (uint32_t)(z >> 16);
+  }
+  K.x0 = k[0];
+  for (int r = 0; r < 4; ++r) {
+    K.mul[r] = (M[r] ^ (k[1 + r] << 1)) | 1u;          // odd multipliers
+    K.add[r] = k[5 + r];
   }
   return K;
 }
@@ -105,14 +111,14 @@ static bool make_plan(int64_t N, int64_t B, EpochPlan* P) {
 
 template <bool HAVE_POS>
 __device__ __forceinline__ uint32_t batch_of(int64_t r, const int32_t* __restrict__ pos, uint32_t N, uint32_t B,
-                                             const FeistelKey& K) {
+                                             const ShuffleKey& K) {
   const uint32_t p = HAVE_POS ? (uint32_t)__ldg(pos + r) : epoch_position((uint32_t)r, N, K);
   return p / B;
 }
 
 template <bool HAVE_POS>
 __global__ void __launch_bounds__(kEpochBlock)
-k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, FeistelKey K, uint32_t* __restrict__ hist) {
+k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K, uint32_t* __restrict__ hist) {
   extern __shared__ uint32_t s_cnt[];                       // [kEpochWarps][nb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* cnt = s_cnt + warp * P.nb;
@@ -135,7 +141,7 @@ k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, FeistelKey K, uint32
 
 template <bool HAVE_POS>
 __global__ void __launch_bounds__(kEpochBlock)
-k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict__ pos, EpochPlan P, FeistelKey K,
+k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K,
                 const uint32_t* __restrict__ offs, mfcd_triplet* __restrict__ out) {
   extern __shared__ uint32_t s_base[];                      // [kEpochWarps][nb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* __restrict__ a, i
   }
 }
 
-__global__ void k_epoch_positions(int64_t N, FeistelKey K, int32_t* __restrict__ pos) {
+__global__ void k_epoch_positions(int64_t N, ShuffleKey K, int32_t* __restrict__ pos) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x)
     pos[r] = (int32_t)epoch_position((uint32_t)r, (uint32_t)N, K);
 }
@@ -314,7 +320,7 @@ extern "C" int mfcd_epoch_batches(const mfcd_triplet* rec, int64_t N, int64_t B,
   cudaStream_t st = as_stream(stream);
   uint32_t* hist = static_cast<uint32_t*>(workspace);
   uint32_t* sums = hist + P.hist_len;
-  const FeistelKey K = make_key(N, seed);
+  const ShuffleKey K = make_key(N, seed);
   const size_t smem = sizeof(uint32_t) * (size_t)kEpochWarps * P.nb;
   const int grid = grid_for(P.n_seg, kEpochWarps, 8);
   if (pos) k_epoch_count<true><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist);

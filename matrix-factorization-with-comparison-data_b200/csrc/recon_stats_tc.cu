@@ -3,16 +3,19 @@
 // Same contract as k_recon_stats (recon_stats.cu; reference structure.py:939-955, :980-1064): one pass over
 // W = U V^T and X that leaves six fp64 sums per row.  X (4 n m bytes) is the only large stream, so the
 // kernel is organised around keeping that stream moving at HBM speed:
-//   * a tiny pre-pass splits U and V into  hi + lo  (hi = top 10 mantissa bits = an exact TF32 value)
-//     K-padded staging tables, and computes the row / column means of W (a_r = <U_r, vbar>,
-//     b_c = <ubar, V_c>);
-//   * ONE producer thread per CTA feeds everything with TMA tensor copies
-//     (cp.async.bulk.tensor.2d, 128-byte swizzle, zero fill outside the matrices): the A tile (128 rows
-//     of U_hi / U_lo) once per row block, and per 128 x 64 tile the B operand (64 rows of V_hi / V_lo)
-//     and, through a separate ring that runs 2-4 tiles ahead (3-5 slots of 32 KB), the matching X tile;
-//   * ONE thread issues tcgen05.mma (kind::tf32, M = 128, N = 64, K = 8 per instruction), three MMAs per
-//     K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's sgemm), accumulating in TMEM
-//     (2 stages x 64 columns);
+//   * a tiny pre-pass splits V into  hi + lo  (hi = top 10 mantissa bits = an exact TF32 value) K-padded
+//     staging tables, and computes the row / column means of W (a_r = <U_r, vbar>, b_c = <ubar, V_c>);
+//   * the A operand (128 rows of U, split hi / lo on the fly) lives in TENSOR MEMORY, not shared memory: at the
+//     start of a row block the epilogue warps read their rows of U from global memory and write them with
+//     tcgen05.st next to the accumulators (TMEM columns [128, 128 + K) = hi, [128 + KMAX, ...) = lo).  That
+//     frees 64 KB of shared memory at K = 64 for a deeper X ring (5 tiles instead of 3: the round-1 profile
+//     showed the X stream starved by a 3-deep ring) and is what makes K = 128 fit at all;
+//   * ONE producer thread per CTA feeds the rest with TMA tensor copies (cp.async.bulk.tensor.2d, 128-byte
+//     swizzle, zero fill outside the matrices): per 128 x 64 tile the B operand (64 rows of V_hi / V_lo) and,
+//     through a separate ring that runs 2-5 tiles ahead (3-6 slots of 32 KB), the matching X tile;
+//   * ONE thread issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory, M = 128, N = 64, K = 8 per
+//     instruction), three MMAs per K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's
+//     sgemm), accumulating in TMEM (2 stages x 64 columns);
 //   * sixteen epilogue warps (TMEM lane quarter = warp id % 4, 16-column quarter = warp id / 4; eight warps
 //     with 32 columns each left the pipeline waiting on the epilogue: 2.5 us per tile against 0.4 for the MMAs) read the
 //     accumulators with tcgen05.ld, the X tile from swizzled shared memory, and fold both into per-row
@@ -27,22 +30,22 @@ namespace tc {
 
 constexpr int TM = 128;                 // tile rows  (UMMA M, TMEM lanes)
 constexpr int TN = 64;                  // tile cols  (UMMA N, TMEM columns per stage)
-constexpr int KMAX = 64;                // largest K handled (2 swizzle slabs)
+constexpr int KMAX = 128;               // largest K handled (4 swizzle slabs of B; A = 2 x 128 TMEM columns)
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
 constexpr int NSTAGE = 2;
 constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 16-column quarter of the tile w / 4
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
-constexpr uint32_t A_SLAB_BYTES = TM * 128;
 constexpr uint32_t B_SLAB_BYTES = TN * 128;
+constexpr uint32_t TMEM_A_HI = NSTAGE * TN;            // TMEM column of the A operand's hi part
+constexpr uint32_t TMEM_A_LO = TMEM_A_HI + KMAX;       // ... and of its lo part
 constexpr uint32_t X_BOX_BYTES = TM * 128;   // 128 rows x 32 columns of X
 
-constexpr int MAX_RING = 5;              // X-tile ring depth (tiles); 3 fit next to K = 64 operands, 5 next to K <= 32
+constexpr int MAX_RING = 6;              // X-tile ring depth (tiles): 6 next to K <= 32, 5 at K = 64, 3 at K = 128
 constexpr uint32_t XSLOT_BYTES = 2 * X_BOX_BYTES;      // one ring slot = the two 32-column boxes of a tile
 
 // Shared-memory plan (all regions 1024-byte aligned, sizes depend on the number of K slabs):
-//   A  : a_hi[nslab], a_lo[nslab]                 16 KB each
 //   B  : 2 stages x (b_hi[nslab], b_lo[nslab])     8 KB each
 //   X  : ring of `ring` tile slots                 32 KB each
 //   tail: b_col[ring][64], mbarriers, TMEM base, error flag
@@ -53,11 +56,12 @@ struct Tail {
   uint32_t tmem_base;
   int error;
 };
-__host__ __device__ constexpr uint32_t a_bytes(int nslab) { return 2u * nslab * A_SLAB_BYTES; }
 __host__ __device__ constexpr uint32_t b_stage_bytes(int nslab) { return 2u * nslab * B_SLAB_BYTES; }
 __host__ __device__ constexpr uint32_t smem_bytes(int nslab, int ring) {
-  return a_bytes(nslab) + NSTAGE * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
+  return NSTAGE * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
 }
+// TMEM columns to allocate (power of two >= 32): 2 accumulator stages + hi and lo of the A operand
+__host__ __device__ constexpr uint32_t tmem_cols(int kpad) { return kpad <= 64 ? 256u : 512u; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -116,6 +120,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = tile row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive TMEM columns of this thread's lane (the warp covers its 32-lane quarter)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -150,7 +169,7 @@ __device__ __forceinline__ void split_table(const float* __restrict__ T, int64_t
                                             const float* __restrict__ other_mean, float* __restrict__ hi,
                                             float* __restrict__ lo, float* __restrict__ dots, int64_t dots_len,
                                             int64_t tid, int64_t nth) {
-  const int64_t total = rows * kpad;
+  const int64_t total = hi ? rows * kpad : 0;          // hi == NULL: only the dots (A is split in the main kernel)
   for (int64_t idx = tid; idx < total; idx += nth) {
     const int64_t r = idx / kpad;
     const int k = (int)(idx - r * kpad);
@@ -169,33 +188,31 @@ __device__ __forceinline__ void split_table(const float* __restrict__ T, int64_t
 
 __global__ void __launch_bounds__(256)
 k_tc_prepass(const float* __restrict__ U, const float* __restrict__ V, int64_t n, int64_t m, int d, int kpad,
-             const float* __restrict__ ubar, const float* __restrict__ vbar, float* __restrict__ u_hi,
-             float* __restrict__ u_lo, float* __restrict__ v_hi, float* __restrict__ v_lo, float* __restrict__ avec,
+             const float* __restrict__ ubar, const float* __restrict__ vbar, float* __restrict__ v_hi,
+             float* __restrict__ v_lo, float* __restrict__ avec,
              float* __restrict__ bvec, int64_t bvec_len, double* __restrict__ row_stats, int* __restrict__ error_flag) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-  split_table(U, n, d, kpad, vbar, u_hi, u_lo, avec, n, tid, nth);
+  split_table(U, n, d, kpad, vbar, nullptr, nullptr, avec, n, tid, nth);
   split_table(V, m, d, kpad, ubar, v_hi, v_lo, bvec, bvec_len, tid, nth);
   for (int64_t k = tid; k < 8 * n; k += nth) row_stats[k] = 0.0;
   if (tid == 0) *error_flag = 0;
 }
 
 struct Maps {
-  CUtensorMap x, u_hi, u_lo, v_hi, v_lo;
+  CUtensorMap x, v_hi, v_lo;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp, int ring, float s,
-                 const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
+k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U, int64_t n, int64_t m, int d, int kp,
+                 int ring, float s, const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
                  double* __restrict__ row_stats, int* __restrict__ error_flag) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with shared-space arithmetic so the compiler keeps LDS/STS addressing
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nslab = (kp + SLAB_K - 1) / SLAB_K;
-  unsigned char* a_hi = base;                                     // [nslab] slabs
-  unsigned char* a_lo = a_hi + nslab * A_SLAB_BYTES;
-  unsigned char* b_base = base + a_bytes(nslab);                  // stage st: b_hi[nslab] then b_lo[nslab]
+  unsigned char* b_base = base;                                   // stage st: b_hi[nslab] then b_lo[nslab]
   unsigned char* x_base = b_base + NSTAGE * b_stage_bytes(nslab); // slot sl: box 0, box 1
   Tail& tl = *reinterpret_cast<Tail*>(x_base + ring * XSLOT_BYTES);
   volatile int* err = &tl.error;
@@ -213,10 +230,10 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
       mbar_init(&tl.mma_done[st], 1);
       mbar_init(&tl.tmem_free[st], EPI_THREADS);
     }
-    mbar_init(&tl.a_full, 1);
+    mbar_init(&tl.a_full, EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP) tmem_alloc(&tl.tmem_base, NSTAGE * TN);
+  if (warp == MMA_WARP) tmem_alloc(&tl.tmem_base, tmem_cols(nslab * SLAB_K));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -248,6 +265,40 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
       const int64_t gr = (int64_t)row0 + t;
       const float a_row = gr < n ? __ldg(avec + gr) : 0.f;
       const int sw = t & 7;
+      {
+        // A operand of this row block -> tensor memory: the thread's row of U, this warp's quarter of the K range,
+        // split into hi (exact TF32) and lo = v - hi, eight columns per tcgen05.st.  The previous row block's MMAs
+        // have completed (work-item barrier below), so the columns are free to overwrite.
+        const int kc = (nslab * SLAB_K) >> 2;                       // K columns per warp quarter: 8, 16, 24 or 32
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float* urow = U + gr * (int64_t)d;
+        const bool vec = (d & 3) == 0;
+        for (int k0 = quarter * kc; k0 < (quarter + 1) * kc; k0 += 8) {
+          float v[8], hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          if (gr < n && k0 < d) {
+            if (vec && k0 + 8 <= d) {
+              const float4 p = __ldg(reinterpret_cast<const float4*>(urow + k0));
+              const float4 q = __ldg(reinterpret_cast<const float4*>(urow + k0 + 4));
+              v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (k0 + e < d) v[e] = __ldg(urow + k0 + e);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+            lo[e] = v[e] - hi[e];
+          }
+          tmem_st8(tmem_base + lane_base + TMEM_A_HI + (uint32_t)k0, hi);
+          tmem_st8(tmem_base + lane_base + TMEM_A_LO + (uint32_t)k0, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&tl.a_full);
+      }
       double acc[6] = {0, 0, 0, 0, 0, 0};
       for (int it = 0; it < ntiles; ++it) {
         const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
@@ -322,12 +373,6 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
           tma_load_2d(dst + X_BOX_BYTES, &maps.x, col0 + SLAB_K, row0, &tl.x_full[slot]);
           bulk_g2s(&tl.b_col[slot][0], bvec + col0, TN * (uint32_t)sizeof(float), &tl.x_full[slot]);   // bvec padded to 64
         };
-        // A tile of this row block; the previous block's MMAs are complete (work-item barrier below)
-        mbar_arrive_expect_tx(&tl.a_full, a_bytes(nslab));
-        for (int sl = 0; sl < nslab; ++sl) {
-          tma_load_2d(a_hi + sl * A_SLAB_BYTES, &maps.u_hi, sl * SLAB_K, row0, &tl.a_full);
-          tma_load_2d(a_lo + sl * A_SLAB_BYTES, &maps.u_lo, sl * SLAB_K, row0, &tl.a_full);
-        }
         for (int it = 0; ok && it < ring - 1 && it < ntiles; ++it) issue_x(it);      // X runs ring-1 tiles ahead
         for (int it = 0; ok && it < ntiles; ++it) {
           const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
@@ -358,14 +403,14 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
           const uint32_t bl = bh + nslab * B_SLAB_BYTES;
           uint32_t accumulate = 0;
           for (int ks = 0; ks < (kp >> 3); ++ks) {
-            const uint32_t slab = ks >> 2, within = (ks & 3) * 32;     // 8 tf32 = 32 bytes per K step
-            const uint64_t d_a_hi = make_desc(smem_u32(a_hi) + slab * A_SLAB_BYTES + within);
-            const uint64_t d_a_lo = make_desc(smem_u32(a_lo) + slab * A_SLAB_BYTES + within);
+            const uint32_t slab = ks >> 2, within = (ks & 3) * 32;     // 8 tf32 = 32 bytes of B = 8 TMEM columns of A per K step
+            const uint32_t t_a_hi = tmem_base + TMEM_A_HI + ks * 8;
+            const uint32_t t_a_lo = tmem_base + TMEM_A_LO + ks * 8;
             const uint64_t d_b_hi = make_desc(bh + slab * B_SLAB_BYTES + within);
             const uint64_t d_b_lo = make_desc(bl + slab * B_SLAB_BYTES + within);
-            umma_tf32(d_tmem, d_a_hi, d_b_hi, idesc, accumulate);
-            umma_tf32(d_tmem, d_a_hi, d_b_lo, idesc, 1u);
-            umma_tf32(d_tmem, d_a_lo, d_b_hi, idesc, 1u);
+            umma_tf32_ts(d_tmem, t_a_hi, d_b_hi, idesc, accumulate);
+            umma_tf32_ts(d_tmem, t_a_hi, d_b_lo, idesc, 1u);
+            umma_tf32_ts(d_tmem, t_a_lo, d_b_hi, idesc, 1u);
             accumulate = 1u;
           }
           umma_commit(&tl.mma_done[st]);   // arrives when the MMAs above have finished (implies fence::before_thread_sync)
@@ -381,7 +426,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, int64_t n, int64_t m, int kp
   }
 
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, NSTAGE * TN);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, tmem_cols(nslab * SLAB_K));
   if (threadIdx.x == 0 && tl.error) atomicExch(error_flag, 1);
 }
 
@@ -418,13 +463,11 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
-static int kpad_for(int d) { return d <= SLAB_K ? SLAB_K : KMAX; }
+static int kpad_for(int d) { return (d + SLAB_K - 1) / SLAB_K * SLAB_K; }      // 32, 64, 96 or 128
 
-struct TcLayout { size_t u_hi, u_lo, v_hi, v_lo, avec, bvec, total; };
+struct TcLayout { size_t v_hi, v_lo, avec, bvec, total; };
 static TcLayout tc_layout(int64_t n, int64_t m, int d) {
   TcLayout L; size_t off = 0; const int kpad = kpad_for(d);
-  L.u_hi = off; off += align_up(sizeof(float) * n * kpad);
-  L.u_lo = off; off += align_up(sizeof(float) * n * kpad);
   L.v_hi = off; off += align_up(sizeof(float) * m * kpad);
   L.v_lo = off; off += align_up(sizeof(float) * m * kpad);
   L.avec = off; off += align_up(sizeof(float) * n);
@@ -456,7 +499,7 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   MFCD_REQUIRE(U && V && X && ubar && vbar && row_stats && error_flag, "mfcd_recon_stats_tc: NULL pointer");
   MFCD_REQUIRE(n >= 1 && m >= 1 && d >= 1, "mfcd_recon_stats_tc: bad sizes");
   if (!tc_eligible(n, m, d, X)) {
-    set_error("mfcd_recon_stats_tc: shape not eligible (needs dense X with 16-byte aligned rows and d <= 64)");
+    set_error("mfcd_recon_stats_tc: shape not eligible (needs dense X with 16-byte aligned rows and d <= 128)");
     return MFCD_ERR_UNSUPPORTED;
   }
   const tc::TcLayout L = tc::tc_layout(n, m, d);
@@ -466,8 +509,6 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   }
   cudaStream_t st = as_stream(stream);
   char* base = static_cast<char*>(workspace);
-  float* u_hi = reinterpret_cast<float*>(base + L.u_hi);
-  float* u_lo = reinterpret_cast<float*>(base + L.u_lo);
   float* v_hi = reinterpret_cast<float*>(base + L.v_hi);
   float* v_lo = reinterpret_cast<float*>(base + L.v_lo);
   float* avec = reinterpret_cast<float*>(base + L.avec);
@@ -478,13 +519,11 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   tc::Maps maps;
   int rc;
   if ((rc = tc::make_map(&maps.x, X->X, n, m, X->ldx, tc::TM)) != MFCD_OK) return rc;
-  if ((rc = tc::make_map(&maps.u_hi, u_hi, n, kpad, kpad, tc::TM)) != MFCD_OK) return rc;
-  if ((rc = tc::make_map(&maps.u_lo, u_lo, n, kpad, kpad, tc::TM)) != MFCD_OK) return rc;
   if ((rc = tc::make_map(&maps.v_hi, v_hi, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
   if ((rc = tc::make_map(&maps.v_lo, v_lo, m, kpad, kpad, tc::TN)) != MFCD_OK) return rc;
 
   const int64_t bvec_len = (m + tc::TN - 1) / tc::TN * tc::TN;
-  tc::k_tc_prepass<<<grid_for((n + m) * kpad, 256, 8), 256, 0, st>>>(U, V, n, m, d, kpad, ubar, vbar, u_hi, u_lo, v_hi,
+  tc::k_tc_prepass<<<grid_for((n + m) * kpad, 256, 8), 256, 0, st>>>(U, V, n, m, d, kpad, ubar, vbar, v_hi,
                                                                      v_lo, avec, bvec, bvec_len, row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
 
@@ -501,7 +540,7 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   while (ring > 2 && tc::smem_bytes(nslab, ring) > 232448u) --ring;
   const size_t smem = tc::smem_bytes(nslab, ring);
   MFCD_CUDA(cudaFuncSetAttribute(tc::k_recon_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, n, m, kp, ring, s, avec, bvec, (int)splits,
+  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, U, n, m, d, kp, ring, s, avec, bvec, (int)splits,
                                                                row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;

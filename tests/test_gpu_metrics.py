@@ -160,7 +160,8 @@ def test_c5_shape_stats_properties(G):
 
 
 @pytest.mark.parametrize("shape", [(128, 64, 8), (300, 260, 32), (1000, 1024, 64), (257, 132, 10), (130, 256, 64),
-                                   (64, 4, 3), (513, 1028, 48), (5, 8, 2), (2000, 36, 17)])
+                                   (64, 4, 3), (513, 1028, 48), (5, 8, 2), (2000, 36, 17), (300, 260, 128),
+                                   (1000, 1024, 128), (257, 132, 100), (130, 256, 65), (700, 2052, 96)])
 def test_tensor_core_recon_stats_matches_simt(G, shape):
     """tcgen05/TMEM engine (tf32 hi/lo split, 3 MMAs) == fp32 SIMT engine on the six per-row sums."""
     from mfcd_b200 import metrics
@@ -190,5 +191,43 @@ def test_tensor_core_engine_rejects_ineligible_shapes(G):
     model = MatrixFactorization(40, 30, 128)
     gt = GroundTruth(X=torch.zeros(40, 30))
     with pytest.raises(MfcdError):
-        metrics._row_stats(model, gt, 1.0, engine="tc")       # d > 64 and rows of X not 16-byte aligned
+        metrics._row_stats(model, gt, 1.0, engine="tc")       # rows of X not 16-byte aligned
     metrics._row_stats(model, gt, 1.0, engine="auto")         # falls back to the SIMT engine
+    model = MatrixFactorization(40, 32, 132)
+    gt = GroundTruth(X=torch.zeros(40, 32))
+    with pytest.raises(MfcdError):
+        metrics._row_stats(model, gt, 1.0, engine="tc")       # d > 128
+    metrics._row_stats(model, gt, 1.0, engine="auto")
+
+
+@pytest.mark.parametrize("shape", [(1000, 1024, 128), (1000, 1024, 64), (515, 1284, 32)])
+def test_tensor_core_recon_stats_against_the_float64_oracle(G, shape):
+    """The tcgen05 engine on multi-tile shapes (A operand in tensor memory, K up to 128) against float64 numpy:
+    the six per-row sums directly, and through them the reference's metrics (structure.py:939-955, :980-996)."""
+    import structure
+    from mfcd_b200 import metrics
+    from mfcd_b200.store import GroundTruth
+    from mfcd_b200.trainer import MatrixFactorization
+    n, m, d = shape
+    rng = np.random.default_rng(n * 3 + d)
+    torch.manual_seed(d)
+    model = MatrixFactorization(n, m, d)
+    U, V = model.U.detach().numpy().astype(np.float64), model.V.detach().numpy().astype(np.float64)
+    Xf = rng.standard_normal((n, m)).astype(np.float32)
+    X = Xf.astype(np.float64)
+    s = 0.7
+    got, _ = metrics._row_stats(model, GroundTruth(X=torch.from_numpy(Xf)), s, engine="tc")
+    W = U @ V.T
+    a = U @ V.mean(axis=0)
+    b = V @ U.mean(axis=0)
+    wa = W - a[:, None]
+    want = np.stack([X.sum(1), (X * X).sum(1), wa.sum(1), (wa * wa).sum(1), (X * wa).sum(1),
+                     ((W - b[None, :] - s * X) ** 2).sum(1)], 1)
+    scale = np.abs(want).max(axis=0)
+    scale[2] = np.sqrt(m * want[:, 3]).max()
+    err = np.abs(got[:, :6] - want).max(axis=0) / scale
+    assert (err < 2e-5).all(), err
+    assert np.abs(got[:, 6] - a).max() < 1e-5
+    rec = structure.compute_reconstruction_error(model, torch.from_numpy(Xf), s)
+    ref = O.reconstruction_error(U.astype(np.float32), V.astype(np.float32), Xf, s)
+    assert abs(rec - ref) < 1e-4 * ref
