@@ -100,8 +100,8 @@ int mfcd_gather_triplets(const mfcd_triplet* rec, const int32_t* perm, int64_t N
 /* ---- epoch batching: the epoch reshuffle and the per-batch user grouping in one streaming pass -------------
  * Replaces RandomSampler + default_collate for one epoch (structure.py:738, :845) at throughput batch sizes.
  * Record r of the store has epoch position pos(r): pos[r] when `pos` is given (int32, the INVERSE of the epoch
- * permutation: see mfcd_invert_perm), else a keyed bijection of [0, N) evaluated on the fly (4 rounds of odd
- * multiply / xor-shift / add over ceil(log2 N) bits, cycle walking; mfcd_epoch_positions writes the same values out).
+ * permutation: see mfcd_invert_perm), else a keyed bijection of [0, N) evaluated on the fly (a 3-round mixed-radix
+ * network over a domain c * 2^k that hugs N, c <= 64; mfcd_epoch_positions writes the same values out).
  * Batch b = { r : pos(r) / B == b } -- exactly the batches a loader that walks the permutation in chunks of B
  * forms (every batch has B members, the last one the remainder).  out[] receives batch 0, batch 1, ... each in
  * STORE order (stable), so a store sorted by user yields user-grouped batches (MFCD_FLAG_USER_GROUPED) for free.

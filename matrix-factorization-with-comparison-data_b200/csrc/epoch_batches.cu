@@ -7,19 +7,21 @@
 // batch by user (what K1's user-run path wants), this file does a stable multisplit:
 //
 //   * record r of the store has epoch position pos(r): pos[r] from memory (the inverse of a given
-//     permutation -- reference RNG mode), or a keyed bijection of [0, N) evaluated on the fly (multiply /
-//     xor-shift / add rounds over ceil(log2 N) bits with cycle walking; device RNG mode);
+//     permutation -- reference RNG mode), or a keyed bijection of [0, N) evaluated on the fly (see ShuffleKey;
+//     device RNG mode);
 //   * batch(r) = pos(r) / B -- exactly the batches a loader walking the permutation in chunks of B forms,
 //     every batch has B members (the last one N - (nb-1) B);
 //   * out[] receives batch after batch, each batch's records in STORE order.  When the store is sorted by
 //     user (done once per dataset) every batch comes out user-grouped for free (MFCD_FLAG_USER_GROUPED).
 //
 // Two kernels over the store + a scan of the (batch x warp-segment) histogram:
-//   k_epoch_count    warp w counts, per batch, the records of its segment                 (reads pos only)
+//   k_epoch_count    warp w derives the batch of every record of its segment, stores it (1 - 2 bytes per record)
+//                    and counts the records per batch
 //   scan             exclusive prefix sum of hist[batch][segment] = final output offsets  (3 small kernels)
-//   k_epoch_scatter  warp w re-derives the batch of each record, ranks it among the equal-batch lanes of its
-//                    32-record tile (match.any), and stores the record at offset[batch] + rank
-// HBM traffic: 16 N read + 16 N written (+ 4 N for pos[] when given) -- the floor of any out-of-place shuffle.
+//   k_epoch_scatter  warp w ranks each record among the equal-batch lanes of its 32-record tile (match.any) and
+//                    stores it at offset[batch] + rank
+// HBM traffic: 16 N read + 16 N written + 2 - 4 N for the batch ids (+ 4 N for pos[] when given) -- close to the
+// floor of any out-of-place shuffle.
 #include "internal.h"
 
 namespace mfcd {
@@ -28,33 +30,47 @@ constexpr int kEpochMaxBatches = 1024;     // counters per warp in shared memory
 constexpr int kEpochBlock = 256;
 constexpr int kEpochWarps = kEpochBlock / 32;
 
-// Keyed bijection of the bits-wide integers: 4 rounds of  x = x * odd (mod 2^bits);  x ^= x >> bits/2;
-// x = x + key (mod 2^bits)  -- each step is invertible, so the composition is a permutation of [0, 2^bits).
-// Multiplication carries information upward, the xor-shift brings the well-mixed top half back down; the batch of
-// a record is pos / B, i.e. it is decided by the best-mixed (high) bits.  ~20 integer instructions per pass, which
-// matters: the first version of this file used an 8-round Feistel network (~100 instructions per pass, ~4.5 passes
-// per warp with cycle walking) and BOTH kernels were ALU-bound (profiles/r02_notes.md: k_epoch_count 68 % issue
-// active, 0 % DRAM; 3.3 ms per epoch of 84 M records against ~0.6 ms of pure data movement).
+// Keyed bijection of [0, M), M = c * 2^k >= N with c <= 64 (so M - N < M / 32: a pass leaves [0, N) with
+// probability < 3 %, and the cycle walk below almost never iterates).  A value is split into hi in [0, c) and
+// lo in [0, 2^k); three rounds of
+//     lo <- ((lo ^ f_r(hi)) * odd_r  mod 2^k) ^ (itself >> k/2), + key_r  mod 2^k     (a bijection of lo for fixed hi)
+//     hi <- hi + g_r(lo)  mod c,  g_r(lo) = mulhi(hash32(lo + key_r), c)               (a bijection of hi for fixed lo)
+// -- every step is invertible, so the composition is a permutation of [0, M).
+// Why this shape: the first version of this file walked an 8-round Feistel network over 2^ceil(log2 N) values
+// (~100 instructions per pass); the second a 4-round multiply / xor-shift chain (~25).  Both reject up to half of
+// their outputs, and a WARP repeats the pass until its slowest lane is inside [0, N): 5.6 - 9 passes per 32 records,
+// which left k_epoch_count and k_epoch_scatter ALU-bound (profiles/r02_notes.md: 380 - 410 warp instructions per
+// tile, 72 % issue-active, 0 - 33 % DRAM).  With a domain that hugs N the walk disappears, and the batch ids are
+// computed ONCE (k_epoch_count stores them for k_epoch_scatter).
 struct ShuffleKey {
-  uint32_t x0, mul[4], add[4];
-  uint32_t bits;      // ceil(log2 N), at least 2, at most 31
+  uint32_t k, c;                      // lo bits (>= 1), hi range (1..64)
+  uint32_t fmul[3], lmul[3], ladd[3], hadd[3];
 };
 
 __host__ __device__ __forceinline__ uint32_t shuffle_once(uint32_t x, const ShuffleKey& K) {
-  const uint32_t mask = (1u << K.bits) - 1u;
-  const uint32_t sh = K.bits >> 1;                     // >= 1
-  x ^= K.x0 & mask;
+  const uint32_t mask = (1u << K.k) - 1u;
+  const uint32_t sh = (K.k >> 1) ? (K.k >> 1) : 1u;
+  uint32_t hi = x >> K.k, lo = x & mask;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    x = (x * K.mul[r]) & mask;
-    x ^= x >> sh;
-    x = (x + K.add[r]) & mask;
+  for (int r = 0; r < 3; ++r) {
+    const uint32_t f = ((hi + 1u) * K.fmul[r]) >> (32u - K.k);
+    lo = ((lo ^ f) * K.lmul[r]) & mask;
+    lo ^= lo >> sh;
+    lo = (lo + K.ladd[r]) & mask;
+    uint32_t h = (lo + K.hadd[r]) * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+#ifdef __CUDA_ARCH__
+    hi += __umulhi(h, K.c);
+#else
+    hi += (uint32_t)(((uint64_t)h * K.c) >> 32);
+#endif
+    if (hi >= K.c) hi -= K.c;
   }
-  return x;
+  return (hi << K.k) | lo;
 }
 
-// bijection of [0, N): walk the cycle of the 2^bits permutation until it re-enters [0, N)  (N > 2^(bits-1), so
-// a pass lands inside with probability > 1/2)
+// bijection of [0, N): walk the cycle of the permutation of [0, M) until it re-enters [0, N)
 __host__ __device__ __forceinline__ uint32_t epoch_position(uint32_t r, uint32_t N, const ShuffleKey& K) {
   uint32_t x = shuffle_once(r, K);
   while (x >= N) x = shuffle_once(x, K);
@@ -65,22 +81,25 @@ static ShuffleKey make_key(int64_t N, uint64_t seed) {
   ShuffleKey K;
   int bits = 2;
   while ((int64_t(1) << bits) < N) ++bits;
-  K.bits = (uint32_t)bits;
-  static const uint32_t M[4] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu};
-  uint32_t k[9];
+  const int k = (bits / 2) > (bits - 6) ? (bits / 2) : (bits - 6);
+  K.k = (uint32_t)k;
+  K.c = (uint32_t)((N + (int64_t(1) << k) - 1) >> k);
+  if (K.c < 1) K.c = 1;
+  uint32_t w[12];
   uint64_t s = seed;
-  for (int r = 0; r < 9; ++r) {          // splitmix64 stream -> 9 key words (bits 16..47 of each output)
+  for (int r = 0; r < 12; ++r) {         // splitmix64 stream -> 12 key words (bits 16..47 of each output)
     s += 0x9E3779B97F4A7C15ull;
     uint64_t z = s;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
-    k[r] = (uint32_t)(z >> 16);
+    w[r] = (uint32_t)(z >> 16);
   }
-  K.x0 = k[0];
-  for (int r = 0; r < 4; ++r) {
-    K.mul[r] = (M[r] ^ (k[1 + r] << 1)) | 1u;          // odd multipliers
-    K.add[r] = k[5 + r];
+  for (int r = 0; r < 3; ++r) {
+    K.fmul[r] = w[3 * r] | 1u;
+    K.lmul[r] = (w[3 * r + 1] << 1) | 1u;            // odd multipliers
+    K.ladd[r] = w[3 * r + 2];
+    K.hadd[r] = w[9 + r];
   }
   return K;
 }
@@ -92,6 +111,7 @@ struct EpochPlan {
   int64_t n_seg;     // warp segments
   int64_t hist_len;  // nb * n_seg
   int64_t n_tiles;   // scan tiles of kScanTile counters
+  int wide;          // batch ids stored as uint16 (more than 256 batches) instead of uint8
 };
 constexpr int kScanTile = 4096;
 
@@ -106,6 +126,7 @@ static bool make_plan(int64_t N, int64_t B, EpochPlan* P) {
   P->n_seg = (N + seg - 1) / seg;
   P->hist_len = nb * P->n_seg;
   P->n_tiles = (P->hist_len + kScanTile - 1) / kScanTile;
+  P->wide = nb > 256;
   return true;
 }
 
@@ -116,9 +137,10 @@ __device__ __forceinline__ uint32_t batch_of(int64_t r, const int32_t* __restric
   return p / B;
 }
 
-template <bool HAVE_POS>
+template <bool HAVE_POS, typename IdT>
 __global__ void __launch_bounds__(kEpochBlock)
-k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K, uint32_t* __restrict__ hist) {
+k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K, uint32_t* __restrict__ hist,
+              IdT* __restrict__ ids) {
   extern __shared__ uint32_t s_cnt[];                       // [kEpochWarps][nb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* cnt = s_cnt + warp * P.nb;
@@ -129,7 +151,11 @@ k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K, uint32
     const int64_t r1 = (r0 + P.seg) < P.N ? (r0 + P.seg) : P.N;
     for (int64_t t = r0; t < r1; t += 32) {
       const int64_t r = t + lane;
-      const uint32_t b = r < r1 ? batch_of<HAVE_POS>(r, pos, (uint32_t)P.N, (uint32_t)P.B, K) : 0xffffffffu;
+      uint32_t b = 0xffffffffu;
+      if (r < r1) {
+        b = batch_of<HAVE_POS>(r, pos, (uint32_t)P.N, (uint32_t)P.B, K);
+        ids[r] = (IdT)b;                                    // computed once: k_epoch_scatter reads it back
+      }
       const uint32_t same = __match_any_sync(0xffffffffu, b);
       if (b != 0xffffffffu && lane == __ffs(same) - 1) cnt[b] += __popc(same);   // one leader per distinct batch
       __syncwarp();
@@ -139,9 +165,9 @@ k_epoch_count(const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K, uint32
   }
 }
 
-template <bool HAVE_POS>
+template <typename IdT>
 __global__ void __launch_bounds__(kEpochBlock)
-k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict__ pos, EpochPlan P, ShuffleKey K,
+k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const IdT* __restrict__ ids, EpochPlan P,
                 const uint32_t* __restrict__ offs, mfcd_triplet* __restrict__ out) {
   extern __shared__ uint32_t s_base[];                      // [kEpochWarps][nb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,12 +178,22 @@ k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict_
     __syncwarp();
     const int64_t r0 = sgm * P.seg;
     const int64_t r1 = (r0 + P.seg) < P.N ? (r0 + P.seg) : P.N;
+    // two tiles in flight: the loads of tile t+1 are issued before tile t is ranked and stored
+    int4 v = make_int4(0, 0, 0, 0);
+    uint32_t b = 0xffffffffu;
+    if (r0 + lane < r1) {
+      v = __ldg(reinterpret_cast<const int4*>(rec) + r0 + lane);
+      b = (uint32_t)__ldg(ids + r0 + lane);
+    }
     for (int64_t t = r0; t < r1; t += 32) {
-      const int64_t r = t + lane;
-      const bool ok = r < r1;
-      int4 v = make_int4(0, 0, 0, 0);
-      if (ok) v = __ldg(reinterpret_cast<const int4*>(rec) + r);
-      const uint32_t b = ok ? batch_of<HAVE_POS>(r, pos, (uint32_t)P.N, (uint32_t)P.B, K) : 0xffffffffu;
+      const int64_t rn = t + 32 + lane;
+      int4 vn = make_int4(0, 0, 0, 0);
+      uint32_t bn = 0xffffffffu;
+      if (rn < r1) {
+        vn = __ldg(reinterpret_cast<const int4*>(rec) + rn);
+        bn = (uint32_t)__ldg(ids + rn);
+      }
+      const bool ok = b != 0xffffffffu;
       const uint32_t same = __match_any_sync(0xffffffffu, b);
       uint32_t dst = 0;
       if (ok) dst = base[b] + __popc(same & lt);            // stable: lower lanes = earlier records
@@ -165,6 +201,7 @@ k_epoch_scatter(const mfcd_triplet* __restrict__ rec, const int32_t* __restrict_
       if (ok && lane == __ffs(same) - 1) base[b] += __popc(same);
       if (ok) reinterpret_cast<int4*>(out)[dst] = v;
       __syncwarp();
+      v = vn; b = bn;
     }
   }
 }
@@ -259,8 +296,11 @@ __global__ void k_invert_perm(const int32_t* __restrict__ perm, int64_t N, int32
     pos[perm[k]] = (int32_t)k;
 }
 
+static size_t epoch_hist_bytes(const EpochPlan& P) {
+  return (sizeof(uint32_t) * (size_t)(P.hist_len + P.n_tiles + 8) + 255) & ~size_t(255);
+}
 static size_t epoch_ws_bytes(const EpochPlan& P) {
-  return sizeof(uint32_t) * (size_t)(P.hist_len + P.n_tiles + 8);
+  return epoch_hist_bytes(P) + (size_t)P.N * (P.wide ? 2 : 1) + 256;
 }
 
 }  // namespace mfcd
@@ -323,8 +363,14 @@ extern "C" int mfcd_epoch_batches(const mfcd_triplet* rec, int64_t N, int64_t B,
   const ShuffleKey K = make_key(N, seed);
   const size_t smem = sizeof(uint32_t) * (size_t)kEpochWarps * P.nb;
   const int grid = grid_for(P.n_seg, kEpochWarps, 8);
-  if (pos) k_epoch_count<true><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist);
-  else k_epoch_count<false><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist);
+  void* ids = static_cast<char*>(workspace) + epoch_hist_bytes(P);
+  if (P.wide) {
+    if (pos) k_epoch_count<true, uint16_t><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist, static_cast<uint16_t*>(ids));
+    else k_epoch_count<false, uint16_t><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist, static_cast<uint16_t*>(ids));
+  } else {
+    if (pos) k_epoch_count<true, uint8_t><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist, static_cast<uint8_t*>(ids));
+    else k_epoch_count<false, uint8_t><<<grid, kEpochBlock, smem, st>>>(pos, P, K, hist, static_cast<uint8_t*>(ids));
+  }
   MFCD_CHECK_LAUNCH();
   k_scan_tile_sums<<<(unsigned)P.n_tiles, 256, 0, st>>>(hist, P.hist_len, sums);
   MFCD_CHECK_LAUNCH();
@@ -332,8 +378,8 @@ extern "C" int mfcd_epoch_batches(const mfcd_triplet* rec, int64_t N, int64_t B,
   MFCD_CHECK_LAUNCH();
   k_scan_tiles<<<(unsigned)P.n_tiles, 1024, 0, st>>>(hist, P.hist_len, sums);
   MFCD_CHECK_LAUNCH();
-  if (pos) k_epoch_scatter<true><<<grid, kEpochBlock, smem, st>>>(rec, pos, P, K, hist, out);
-  else k_epoch_scatter<false><<<grid, kEpochBlock, smem, st>>>(rec, pos, P, K, hist, out);
+  if (P.wide) k_epoch_scatter<uint16_t><<<grid, kEpochBlock, smem, st>>>(rec, static_cast<const uint16_t*>(ids), P, hist, out);
+  else k_epoch_scatter<uint8_t><<<grid, kEpochBlock, smem, st>>>(rec, static_cast<const uint8_t*>(ids), P, hist, out);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }

@@ -1,18 +1,18 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the epoch batching of csrc/epoch_batches.cu.
 
 The reference reshuffles with torch's RandomSampler (structure.py:738); in device RNG mode the product path
-replaces the materialised permutation by a keyed bijection of [0, N) (4 rounds of odd multiply / xor-shift / add
-over ceil(log2 N) bits, with cycle walking) and forms batch b = {r : pos(r) // B == b}, each batch in store order.
+replaces the materialised permutation by a keyed bijection of [0, N) (a 3-round mixed-radix network over a domain
+c * 2^k that hugs N, with cycle walking for the few values that leave [0, N)) and forms batch b = {r : pos(r) // B == b}, each batch in store order.
 This file restates both so that the tests can check the kernels bit for bit (index work), and so that a test can
 rebuild the exact batches an epoch visits and replay them through the training oracle.
 Imported by tests/ only.
 """
 import numpy as np
 
-MULS = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F)
+U32 = np.uint64(0xFFFFFFFF)
 
 
-def round_keys(seed, count=9):
+def round_keys(seed, count=12):
     """splitmix64 stream -> key words (bits 16..47 of each output)"""
     keys = []
     s = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -26,30 +26,43 @@ def round_keys(seed, count=9):
     return keys
 
 
-def _once(x, keys, bits):
-    """one pass of the bijection of the bits-wide integers: xor key, then 4 x (odd multiply, xor-shift, add key)"""
-    mask = np.uint64((1 << bits) - 1)
-    sh = np.uint64(bits >> 1)
-    x = x ^ (np.uint64(keys[0]) & mask)
-    for r in range(4):
-        mul = np.uint64(((MULS[r] ^ ((keys[1 + r] << 1) & 0xFFFFFFFF)) | 1))
-        x = (x * mul) & mask
-        x = x ^ (x >> sh)
-        x = (x + np.uint64(keys[5 + r])) & mask
-    return x
+def domain(N):
+    """(k, c): the bijection lives on [0, c * 2^k), the smallest such range >= N with c <= 64"""
+    bits = 2
+    while (1 << bits) < N:
+        bits += 1
+    k = max(bits // 2, bits - 6)
+    return k, max(1, (N + (1 << k) - 1) >> k)
+
+
+def _once(x, w, k, c):
+    """one pass of the permutation of [0, c * 2^k): three rounds of (lo-mix keyed by hi, hi-add keyed by lo)"""
+    mask = np.uint64((1 << k) - 1)
+    sh = np.uint64(max(k >> 1, 1))
+    kk, cc = np.uint64(k), np.uint64(c)
+    hi, lo = x >> kk, x & mask
+    for r in range(3):
+        f = (((hi + np.uint64(1)) * np.uint64(w[3 * r] | 1)) & U32) >> np.uint64(32 - k)
+        lo = ((lo ^ f) * np.uint64(((w[3 * r + 1] << 1) | 1) & 0xFFFFFFFF)) & mask
+        lo = lo ^ (lo >> sh)
+        lo = (lo + np.uint64(w[3 * r + 2])) & mask
+        h = ((lo + np.uint64(w[9 + r])) * np.uint64(0x9E3779B1)) & U32
+        h = h ^ (h >> np.uint64(15))
+        h = (h * np.uint64(0x85EBCA77)) & U32
+        hi = hi + ((h * cc) >> np.uint64(32))
+        hi = np.where(hi >= cc, hi - cc, hi)
+    return (hi << kk) | lo
 
 
 def epoch_positions(N, seed):
     """pos[r] for r in [0, N): a permutation of [0, N)."""
     N = int(N)
-    bits = 2
-    while (1 << bits) < N:
-        bits += 1
-    keys = round_keys(seed)
-    x = _once(np.arange(N, dtype=np.uint64), keys, bits)
+    k, c = domain(N)
+    w = round_keys(seed)
+    x = _once(np.arange(N, dtype=np.uint64), w, k, c)
     todo = np.nonzero(x >= N)[0]
     while todo.size:
-        x[todo] = _once(x[todo], keys, bits)
+        x[todo] = _once(x[todo], w, k, c)
         todo = todo[x[todo] >= N]
     return x.astype(np.int64)
 
