@@ -23,6 +23,7 @@
 // mbarriers connect the roles; every wait is bounded, so a pipeline bug raises an error flag and lets
 // the kernel drain instead of hanging the GPU.
 #include <cuda.h>
+#include <stdlib.h>
 #include "internal.h"
 
 namespace mfcd {
@@ -32,7 +33,8 @@ constexpr int TM = 128;                 // tile rows  (UMMA M, TMEM lanes)
 constexpr int TN = 64;                  // tile cols  (UMMA N, TMEM columns per stage)
 constexpr int KMAX = 128;               // largest K handled (4 swizzle slabs of B; A = 2 x 128 TMEM columns)
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 2;                // TMEM accumulator stages
+constexpr int MAX_BSTAGE = 4;            // shared-memory stages of the B operand (2 - 4, by K)
 constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 16-column quarter of the tile w / 4
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
@@ -46,19 +48,21 @@ constexpr int MAX_RING = 6;              // X-tile ring depth (tiles): 6 next to
 constexpr uint32_t XSLOT_BYTES = 2 * X_BOX_BYTES;      // one ring slot = the two 32-column boxes of a tile
 
 // Shared-memory plan (all regions 1024-byte aligned, sizes depend on the number of K slabs):
-//   B  : 2 stages x (b_hi[nslab], b_lo[nslab])     8 KB each
+//   B  : 2-4 stages x (b_hi[nslab], b_lo[nslab])   8 KB each.  The B tile of tile t+nbst is requested when the MMAs of
+//        tile t complete, so with 2 stages the L2 latency of a 32 KB operand tile sat on the critical path (round-2
+//        profile at K = 64: DRAM 39 %, tensor pipe 29 %, issue 45 % -- nothing saturated, tile period 1.6 us)
 //   X  : ring of `ring` tile slots                 32 KB each
 //   tail: b_col[ring][64], mbarriers, TMEM base, error flag
 struct Tail {
   float b_col[MAX_RING][TN];
   unsigned long long x_full[MAX_RING], x_free[MAX_RING];
-  unsigned long long b_full[NSTAGE], mma_done[NSTAGE], tmem_free[NSTAGE], a_full;
+  unsigned long long b_full[MAX_BSTAGE], b_free[MAX_BSTAGE], mma_done[NSTAGE], tmem_free[NSTAGE], a_full;
   uint32_t tmem_base;
   int error;
 };
 __host__ __device__ constexpr uint32_t b_stage_bytes(int nslab) { return 2u * nslab * B_SLAB_BYTES; }
-__host__ __device__ constexpr uint32_t smem_bytes(int nslab, int ring) {
-  return NSTAGE * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
+__host__ __device__ constexpr uint32_t smem_bytes(int nslab, int nbst, int ring) {
+  return nbst * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
 }
 // TMEM columns to allocate (power of two >= 32): 2 accumulator stages + hi and lo of the A operand
 __host__ __device__ constexpr uint32_t tmem_cols(int kpad) { return kpad <= 64 ? 256u : 512u; }
@@ -205,7 +209,7 @@ struct Maps {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U, int64_t n, int64_t m, int d, int kp,
-                 int ring, float s, const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
+                 int nbst, int ring, float s, const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
                  double* __restrict__ row_stats, int* __restrict__ error_flag) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with shared-space arithmetic so the compiler keeps LDS/STS addressing
@@ -213,7 +217,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nslab = (kp + SLAB_K - 1) / SLAB_K;
   unsigned char* b_base = base;                                   // stage st: b_hi[nslab] then b_lo[nslab]
-  unsigned char* x_base = b_base + NSTAGE * b_stage_bytes(nslab); // slot sl: box 0, box 1
+  unsigned char* x_base = b_base + nbst * b_stage_bytes(nslab);   // slot sl: box 0, box 1
   Tail& tl = *reinterpret_cast<Tail*>(x_base + ring * XSLOT_BYTES);
   volatile int* err = &tl.error;
   const int64_t row_tiles = (n + TM - 1) / TM;
@@ -225,8 +229,11 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       mbar_init(&tl.x_full[k], 1);
       mbar_init(&tl.x_free[k], EPI_THREADS);
     }
-    for (int st = 0; st < NSTAGE; ++st) {
+    for (int st = 0; st < MAX_BSTAGE; ++st) {
       mbar_init(&tl.b_full[st], 1);
+      mbar_init(&tl.b_free[st], 1);
+    }
+    for (int st = 0; st < NSTAGE; ++st) {
       mbar_init(&tl.mma_done[st], 1);
       mbar_init(&tl.tmem_free[st], EPI_THREADS);
     }
@@ -375,15 +382,15 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
         };
         for (int it = 0; ok && it < ring - 1 && it < ntiles; ++it) issue_x(it);      // X runs ring-1 tiles ahead
         for (int it = 0; ok && it < ntiles; ++it) {
-          const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
+          const uint32_t u = use + it, bs = u % (uint32_t)nbst, bph = (u / (uint32_t)nbst) & 1;
           const int col0 = (int)((ct_begin + it) * TN);
-          if (u >= NSTAGE && !mbar_wait(&tl.mma_done[st], ph ^ 1, err)) break;       // B stage free again
-          mbar_arrive_expect_tx(&tl.b_full[st], b_stage_bytes(nslab));
-          unsigned char* bh = b_base + st * b_stage_bytes(nslab);
+          if (u >= (uint32_t)nbst && !mbar_wait(&tl.b_free[bs], bph ^ 1, err)) break;   // B stage free again
+          mbar_arrive_expect_tx(&tl.b_full[bs], b_stage_bytes(nslab));
+          unsigned char* bh = b_base + bs * b_stage_bytes(nslab);
           unsigned char* bl = bh + nslab * B_SLAB_BYTES;
           for (int sl = 0; sl < nslab; ++sl) {
-            tma_load_2d(bh + sl * B_SLAB_BYTES, &maps.v_hi, sl * SLAB_K, col0, &tl.b_full[st]);
-            tma_load_2d(bl + sl * B_SLAB_BYTES, &maps.v_lo, sl * SLAB_K, col0, &tl.b_full[st]);
+            tma_load_2d(bh + sl * B_SLAB_BYTES, &maps.v_hi, sl * SLAB_K, col0, &tl.b_full[bs]);
+            tma_load_2d(bl + sl * B_SLAB_BYTES, &maps.v_lo, sl * SLAB_K, col0, &tl.b_full[bs]);
           }
           if (it + ring - 1 < ntiles) issue_x(it + ring - 1);
         }
@@ -395,11 +402,12 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
         bool ok = mbar_wait(&tl.a_full, item & 1, err);
         for (int it = 0; ok && it < ntiles; ++it) {
           const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
-          if (!mbar_wait(&tl.b_full[st], ph, err)) break;
+          const uint32_t bs = u % (uint32_t)nbst, bph = (u / (uint32_t)nbst) & 1;
+          if (!mbar_wait(&tl.b_full[bs], bph, err)) break;
           if (u >= NSTAGE && !mbar_wait(&tl.tmem_free[st], ph ^ 1, err)) break;      // TMEM stage drained
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + st * TN;
-          const uint32_t bh = smem_u32(b_base + st * b_stage_bytes(nslab));
+          const uint32_t bh = smem_u32(b_base + bs * b_stage_bytes(nslab));
           const uint32_t bl = bh + nslab * B_SLAB_BYTES;
           uint32_t accumulate = 0;
           for (int ks = 0; ks < (kp >> 3); ++ks) {
@@ -413,7 +421,8 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
             umma_tf32_ts(d_tmem, t_a_lo, d_b_hi, idesc, 1u);
             accumulate = 1u;
           }
-          umma_commit(&tl.mma_done[st]);   // arrives when the MMAs above have finished (implies fence::before_thread_sync)
+          umma_commit(&tl.b_free[bs]);     // both arrive when the MMAs above have finished (implies fence::before_thread_sync):
+          umma_commit(&tl.mma_done[st]);   // the B stage can be refilled, the accumulators can be read
         }
       }
       __syncwarp();
@@ -536,11 +545,20 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   int64_t blocks = row_tiles * splits;
   if (blocks > sms) blocks = sms;                                // persistent: one CTA per SM
   const int nslab = kpad / tc::SLAB_K;
+  // shared-memory split between B stages and X ring slots (both want ~3 tiles in flight), by operand size
+  static const int kBst[5] = {0, 4, 3, 2, 2};
+  int nbst = kBst[nslab];
+  if (getenv("MFCD_K5_BSTAGES")) nbst = atoi(getenv("MFCD_K5_BSTAGES"));
+  if (nbst < 2) nbst = 2;
+  if (nbst > tc::MAX_BSTAGE) nbst = tc::MAX_BSTAGE;
+  while (nbst > 2 && tc::smem_bytes(nslab, nbst, 2) > 232448u) --nbst;
   int ring = tc::MAX_RING;                                       // deepest X ring that fits in 227 KB
-  while (ring > 2 && tc::smem_bytes(nslab, ring) > 232448u) --ring;
-  const size_t smem = tc::smem_bytes(nslab, ring);
+  if (getenv("MFCD_K5_RING")) ring = atoi(getenv("MFCD_K5_RING"));
+  if (ring > tc::MAX_RING) ring = tc::MAX_RING;
+  while (ring > 2 && tc::smem_bytes(nslab, nbst, ring) > 232448u) --ring;
+  const size_t smem = tc::smem_bytes(nslab, nbst, ring);
   MFCD_CUDA(cudaFuncSetAttribute(tc::k_recon_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, U, n, m, d, kp, ring, s, avec, bvec, (int)splits,
+  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, U, n, m, d, kp, nbst, ring, s, avec, bvec, (int)splits,
                                                                row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
