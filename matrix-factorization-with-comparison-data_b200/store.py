@@ -281,7 +281,16 @@ class TripletLoader:
 
     def begin_iteration(self):
         """What `iter(DataLoader)` does to the global RNG, then the epoch order:
-        returns an int32 device permutation, or None when not shuffling."""
+        returns an int32 device permutation, or None when not shuffling.  Draws recorded ahead of time
+        (record_draws) are replayed first."""
+        tape = self.__dict__.get("_tape")
+        if tape:
+            kind, value = tape.popleft()
+            assert kind == "iter", "recorded draws are consumed in the order they were recorded"
+            return value
+        return self._draw_iteration()
+
+    def _draw_iteration(self):
         if self.replay_iter_seed:
             torch.empty((), dtype=torch.int64).random_()                          # _base_seed
         if not self.shuffle:
@@ -295,6 +304,41 @@ class TripletLoader:
             return perm.to(self.store.device, torch.int32)
         with torch.cuda.device(self.store.device):
             return torch.randperm(N, device=self.store.device, dtype=torch.int32)
+
+    def _draw_epoch_seed(self):
+        """device RNG: the seed of an epoch's keyed bijection (one draw from the global CPU generator)"""
+        tape = self.__dict__.get("_tape")
+        if tape:
+            kind, value = tape.popleft()
+            assert kind == "seed", "recorded draws are consumed in the order they were recorded"
+            return value
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def uses_epoch_records(self, batch_size=None, atomic=True):
+        """True when an epoch at this batch size takes the one-pass shuffle + grouping (epoch_records)."""
+        B = int(batch_size or self.batch_size)
+        N = len(self.store)
+        if not atomic or B <= 256 or N == 0 or N >= (1 << 31):
+            return False
+        if not self.shuffle:
+            return True
+        cap = C.c_int32(0)
+        check(lib.mfcd_epoch_max_batches(C.byref(cap)), "mfcd_epoch_max_batches")
+        return (N + B - 1) // B <= cap.value
+
+    def record_draws(self, count=1, batch_size=None, atomic=True):
+        """Make, NOW and in order, the generator draws that `count` future epochs / iterations of this loader would
+        make, and replay them later: lets a sweep prepare experiments sequentially (so the global RNG streams are
+        consumed exactly as in a sequential run) and run their GPU work concurrently."""
+        import collections
+        tape = self.__dict__.setdefault("_tape", collections.deque())
+        seed_kind = (self.shuffle and self.shuffle_rng != "reference"
+                     and self.uses_epoch_records(batch_size, atomic))
+        for _ in range(count):
+            if seed_kind:
+                tape.append(("seed", int(torch.randint(0, 2 ** 62, (1,)).item())))
+            else:
+                tape.append(("iter", self._draw_iteration()))
 
     def epoch_perm(self):
         return self.begin_iteration()
@@ -332,12 +376,9 @@ class TripletLoader:
         if N == 0:
             return None
         if not self.shuffle:
-            if self.replay_iter_seed:
-                torch.empty((), dtype=torch.int64).random_()
+            self.begin_iteration()
             return self.store, self.store.k1_flags(B)
-        cap = C.c_int32(0)
-        check(lib.mfcd_epoch_max_batches(C.byref(cap)), "mfcd_epoch_max_batches")
-        if (N + B - 1) // B > cap.value or N >= (1 << 31):
+        if not self.uses_epoch_records(B):
             return None
         dev = self.store.device
         rec, order = self._user_sorted()
@@ -350,9 +391,7 @@ class TripletLoader:
                 pos = pos0[order].contiguous()                # position of every record of the SORTED copy
             seed = 0
         elif seed is None:
-            if self.replay_iter_seed:
-                torch.empty((), dtype=torch.int64).random_()
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            seed = self._draw_epoch_seed()
         need = C.c_size_t(0)
         check(lib.mfcd_epoch_batches_workspace(N, B, C.byref(need)), "mfcd_epoch_batches_workspace")
         with torch.cuda.device(dev):

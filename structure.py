@@ -89,12 +89,19 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
                    open_browser=False, linear=False, K=1, d1=None,
                    save_path=None, save_every=None, popularity_method="zipf",
                    alpha=1.5, soft_label=False, generation="base", *,
-                   batch_size=64, mode=None, world_size=None, concurrency=None):
+                   batch_size=64, mode=None, world_size=None, concurrency=None, devices=None):
     """Grid (default) or synchronised linear sweep over scalar-or-list arguments;
     one ``run_experiment`` per configuration.  Returns ``[{'params', 'results'}]``
     -- or ``[]`` when ``save_path`` is set, because saved chunks are dropped from
     memory exactly like the reference does (structure.py:186, :200-202).  An
-    existing ``save_path`` is deleted first (:151-153)."""
+    existing ``save_path`` is deleted first (:151-153).
+
+    Keyword-only extras (reference behaviour by default): ``batch_size`` / ``mode`` / ``world_size`` are forwarded to
+    run_experiment; ``concurrency`` = k > 1 keeps up to k repetitions in flight on separate CUDA streams (default: env
+    MFCD_SWEEP_CONCURRENCY, else sequential), ``devices`` = "all" or a list of CUDA devices spreads them over the
+    GPUs of the box.  Results are identical to the sequential sweep and come back in the same order."""
+    if concurrency is None and os.environ.get("MFCD_SWEEP_CONCURRENCY"):
+        concurrency = int(os.environ["MFCD_SWEEP_CONCURRENCY"])
     grid, lists, synchronised = _normalise_grid(dict(zip(_SCAN_KEYS, (
         n, m, d, p, lr, weight_decay, num_epochs, reps, s, K, d1, strategy, popularity_method, alpha,
         soft_label, generation))))
@@ -111,6 +118,9 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
     else:
         raise ValueError("The linear scan is not possible because the parameters are not synchronized.")
 
+    if concurrency is not None and int(concurrency) > 1 and _trainer.dist_world(world_size)[1] == 1:
+        return _scan_concurrent(configs, device, open_browser, batch_size, mode, int(concurrency), devices,
+                                save_path, save_every)
     pending = []
     for cfg in configs:
         print(f"\nRunning experiment with parameters: {cfg}")
@@ -124,6 +134,94 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
         if save_path and save_every and len(pending) >= save_every:
             _append_pickle(save_path, pending)
             pending = []
+    if save_path and pending:
+        _append_pickle(save_path, pending)
+        pending = []
+    return pending
+
+
+def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrency, devices, save_path, save_every):
+    """The sweep with up to ``concurrency`` repetitions in flight.
+
+    A reference-sized experiment leaves most of a B200 idle (its persistent epoch kernel runs on ~10 of 148 SMs), and
+    the reference's sweeps are thousands of such experiments.  Every repetition is PREPARED on the calling thread, in
+    the sequential order -- that is where the host generators are consumed (ground truth, triplets, labels, split,
+    model initialisation, and, recorded ahead of time, the per-epoch loader draws) -- and its GPU work (training,
+    evaluation, metrics) runs on a worker thread with its own CUDA stream, round-robin over ``devices``.  Results
+    come back in the reference's order and are IDENTICAL to a sequential run under the same seeds."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    if devices is None:
+        devs = [compute_device(device)]
+    elif devices == "all":
+        devs = [torch.device("cuda", k) for k in range(torch.cuda.device_count())]
+    else:
+        devs = [torch.device(x) for x in devices]
+    slots = threading.Semaphore(concurrency)
+    local = threading.local()
+
+    def work(P, dev, ready, is_last):
+        try:
+            with torch.cuda.device(dev):
+                streams = local.__dict__.setdefault("streams", {})
+                if dev not in streams:
+                    streams[dev] = torch.cuda.Stream(device=dev)
+                st = streams[dev]
+                st.wait_event(ready)                       # the preparation ran on the caller's stream
+                with torch.cuda.stream(st):
+                    values = _finish_rep(P, is_last=is_last, open_browser=open_browser, progress=False)
+                    st.synchronize()
+                return values
+        finally:
+            slots.release()
+
+    jobs = []                                              # (cfg, [future per repetition])
+    unit = 0
+    with ThreadPoolExecutor(max_workers=concurrency) as pool:
+        pending, done_upto = [], 0
+
+        def flush(block):
+            """move finished experiments, in order, to `pending`; save chunks like the sequential loop does"""
+            nonlocal done_upto, pending
+            while done_upto < len(jobs):
+                cfg, futs = jobs[done_upto]
+                if not block and not all(f.done() for f in futs):
+                    break
+                out = {key: [] for key in _RESULT_KEYS}
+                for f in futs:
+                    values = f.result()
+                    for key in _RESULT_KEYS:
+                        out[key].append(values[key])
+                pending.append({'params': cfg, 'results': out})
+                jobs[done_upto] = (cfg, [])
+                done_upto += 1
+                if save_path and save_every and len(pending) >= save_every:
+                    _append_pickle(save_path, pending)
+                    pending = []
+
+        for cfg in configs:
+            print(f"\nRunning experiment with parameters: {cfg}")
+            futs = []
+            for rep in range(cfg['reps']):
+                slots.acquire()
+                dev = devs[unit % len(devs)]
+                unit += 1
+                try:
+                    with torch.cuda.device(dev):
+                        dev_arg = device if len(devs) == 1 else dev
+                        P = _prepare_rep(cfg['n'], cfg['m'], cfg['d'], cfg['p'], cfg['s'], dev_arg, cfg['lr'],
+                                         cfg['weight_decay'], cfg['num_epochs'], cfg['K'], cfg['strategy'],
+                                         cfg['popularity_method'], cfg['alpha'], cfg['soft_label'], cfg['generation'],
+                                         batch_size, mode, 0, 1, record=True)
+                        ready = torch.cuda.Event()
+                        ready.record(torch.cuda.current_stream(dev))
+                except BaseException:
+                    slots.release()
+                    raise
+                futs.append(pool.submit(work, P, dev, ready, rep == cfg['reps'] - 1))
+            jobs.append((cfg, futs))
+            flush(block=False)
+        flush(block=True)
     if save_path and pending:
         _append_pickle(save_path, pending)
         pending = []
@@ -161,6 +259,69 @@ _RESULT_KEYS = (
     "sampled_UVT_rows", "sampled_X_rows")
 
 
+def _prepare_rep(n, m, d, p, s, device, lr, weight_decay, num_epochs, K, strategy, popularity_method, alpha,
+                 soft_label, generation, batch_size, mode, rank, world, record):
+    """The part of one repetition that consumes the host generators: ground truth, triplets, labels, split, model
+    initialisation (structure.py:353-364).  record=True additionally makes, now and in the sequential order, the
+    draws the rest of the repetition would make (per-epoch loader seeds / permutations, the two sampled row
+    indices), so the GPU work can run later -- concurrently with other experiments -- on the same random streams."""
+    if world > 1:
+        base = _common_seed()
+        torch.manual_seed(base)                      # the same ground truth on every rank
+    X = generate_X(n, m, d, device, generation=generation)
+    num_triplets = int(n * m * p / 2)
+    if world > 1:
+        torch.manual_seed(base + 1000003 * (rank + 1))   # per-rank sampling / label streams
+    train_loader, val_loader, test_loader = split_dataset_from_triplets(
+        X, num_triplets, scale=s, K=K, batch_size=batch_size, strategy=strategy,
+        popularity_method=popularity_method, alpha=alpha, soft_label=soft_label, world_size=world)
+    if world > 1:
+        torch.manual_seed(base + 1)                  # common stream again: model init, sampled rows
+    model = MatrixFactorization(n, m, d).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    P = dict(X=X, s=s, device=device, loaders=(train_loader, val_loader, test_loader), model=model,
+             optimizer=optimizer, num_epochs=num_epochs, mode=mode, world=world, rand_indices=None)
+    if record:
+        atomic = _trainer.resolve_mode(_cfg.SCATTER_MODE if mode is None else mode, batch_size) == _trainer.MODE_ATOMIC
+        for _ in range(num_epochs):                  # train_model: one training and one validation iterator per epoch
+            train_loader.record_draws(1, batch_size, atomic)
+            val_loader.record_draws(1)
+        test_loader.record_draws(1)                  # evaluate_model
+        P["rand_indices"] = torch.randperm(X.shape[0])[:2]
+        test_loader.record_draws(1)                  # compute_ground_truth_metrics
+    return P
+
+
+def _finish_rep(P, is_last=False, open_browser=False, progress=True):
+    """Train, evaluate and measure one prepared repetition (structure.py:368-409) -> {result key: value}."""
+    X, s, device, model, world = P["X"], P["s"], P["device"], P["model"], P["world"]
+    train_loader, val_loader, test_loader = P["loaders"]
+    t_losses, v_losses = _trainer.train_model(
+        model, train_loader, val_loader, P["optimizer"], device, num_epochs=P["num_epochs"], is_last=is_last,
+        open_browser=open_browser, mode=_cfg.SCATTER_MODE if P["mode"] is None else P["mode"], progress=progress,
+        world_size=world)
+    test_loss, test_acc = evaluate_model(model, test_loader, device, world_size=world)
+    rec_error = compute_reconstruction_error(model, X, s, world_size=world)
+    (alpha_val, norm_X_val, norm_ratio_val, rec_scaled, pearson_mean, pearson_std, spearman_mean,
+     spearman_std, svd_err, slopes, correlations, spearman_scores, rec_scaled_per_row,
+     alpha_per_row) = compute_alpha_and_norm_ratios(model, X, world_size=world)
+    rand_indices = P["rand_indices"]
+    if rand_indices is None:
+        rand_indices = torch.randperm(X.shape[0])[:2]                     # structure.py:390
+    sampled_X_rows, sampled_UVT_rows = _metrics.sampled_rows(model, X, rand_indices.tolist())
+    gt_loss, gt_acc = compute_ground_truth_metrics(test_loader, X, device, world_size=world)
+    return dict((
+        ("reconstruction_errors", rec_error), ("log_likelihoods", -test_loss), ("accuracy", test_acc),
+        ("gt_log_likelihoods", -gt_loss), ("gt_accuracy", gt_acc), ("train_losses", t_losses),
+        ("val_losses", v_losses), ("alpha", alpha_val), ("norm_X", norm_X_val),
+        ("norm_ratio", norm_ratio_val), ("reconstruction_error_scaled", rec_scaled),
+        ("pearson_corr", pearson_mean), ("pearson_std", pearson_std), ("spearman_corr", spearman_mean),
+        ("spearman_std", spearman_std), ("svd_error_scaled", svd_err), ("slopes", slopes),
+        ("pearson_corr_matrix", correlations), ("spearman_corr_matrix", spearman_scores),
+        ("reconstruction_error_scaled_per_row", rec_scaled_per_row), ("alpha_per_row", alpha_per_row),
+        ("sampled_UVT_rows", sampled_UVT_rows), ("sampled_X_rows", sampled_X_rows)))
+
+
 def run_experiment(n, m, d, p, s, device, lr, weight_decay, reps=5, num_epochs=100, open_browser=False, K=1,
                    d1=None, strategy="random", popularity_method="zipf", alpha=1.5, soft_label=False,
                    generation="base", *, batch_size=64, mode=None, world_size=None):
@@ -177,44 +338,11 @@ def run_experiment(n, m, d, p, s, device, lr, weight_decay, reps=5, num_epochs=1
     for rep in range(reps):
         if d1 is None:
             d1 = d
-        if world > 1:
-            base = _common_seed()
-            torch.manual_seed(base)                      # the same ground truth on every rank
-        X = generate_X(n, m, d, device, generation=generation)
-        num_triplets = int(n * m * p / 2)
-        if world > 1:
-            torch.manual_seed(base + 1000003 * (rank + 1))   # per-rank sampling / label streams
-        train_loader, val_loader, test_loader = split_dataset_from_triplets(
-            X, num_triplets, scale=s, K=K, batch_size=batch_size, strategy=strategy,
-            popularity_method=popularity_method, alpha=alpha, soft_label=soft_label, world_size=world)
-        if world > 1:
-            torch.manual_seed(base + 1)                  # common stream again: model init, sampled rows
-
-        model = MatrixFactorization(n, m, d).to(device)
-        optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
-        t_losses, v_losses = train_model(model, train_loader, val_loader, optimizer, device,
-                                         num_epochs=num_epochs, is_last=(rep == reps - 1),
-                                         open_browser=open_browser, mode=mode, world_size=world)
-        test_loss, test_acc = evaluate_model(model, test_loader, device, world_size=world)
-        rec_error = compute_reconstruction_error(model, X, s, world_size=world)
-        (alpha_val, norm_X_val, norm_ratio_val, rec_scaled, pearson_mean, pearson_std, spearman_mean,
-         spearman_std, svd_err, slopes, correlations, spearman_scores, rec_scaled_per_row,
-         alpha_per_row) = compute_alpha_and_norm_ratios(model, X, world_size=world)
-        rand_indices = torch.randperm(X.shape[0])[:2]                     # structure.py:390
-        sampled_X_rows, sampled_UVT_rows = _metrics.sampled_rows(model, X, rand_indices.tolist())
-        gt_loss, gt_acc = compute_ground_truth_metrics(test_loader, X, device, world_size=world)
-
-        for key, value in (
-                ("reconstruction_errors", rec_error), ("log_likelihoods", -test_loss), ("accuracy", test_acc),
-                ("gt_log_likelihoods", -gt_loss), ("gt_accuracy", gt_acc), ("train_losses", t_losses),
-                ("val_losses", v_losses), ("alpha", alpha_val), ("norm_X", norm_X_val),
-                ("norm_ratio", norm_ratio_val), ("reconstruction_error_scaled", rec_scaled),
-                ("pearson_corr", pearson_mean), ("pearson_std", pearson_std), ("spearman_corr", spearman_mean),
-                ("spearman_std", spearman_std), ("svd_error_scaled", svd_err), ("slopes", slopes),
-                ("pearson_corr_matrix", correlations), ("spearman_corr_matrix", spearman_scores),
-                ("reconstruction_error_scaled_per_row", rec_scaled_per_row), ("alpha_per_row", alpha_per_row),
-                ("sampled_UVT_rows", sampled_UVT_rows), ("sampled_X_rows", sampled_X_rows)):
-            out[key].append(value)
+        P = _prepare_rep(n, m, d, p, s, device, lr, weight_decay, num_epochs, K, strategy, popularity_method, alpha,
+                         soft_label, generation, batch_size, mode, rank, world, record=False)
+        values = _finish_rep(P, is_last=(rep == reps - 1), open_browser=open_browser)
+        for key in _RESULT_KEYS:
+            out[key].append(values[key])
     return out
 
 
