@@ -183,7 +183,10 @@ def generate_embeddings(n, m, d, device="cpu"):
         U = ortho_group.rvs(dim=n)
         V = ortho_group.rvs(dim=m)
         X = (U @ S @ V.T) * np.sqrt(n * m) / 2
-        return torch.tensor(X, dtype=torch.float32, device=device)
+        Xt = torch.tensor(X, dtype=torch.float32, device=device)
+        return _GroundTruth.attach_factors(Xt, torch.tensor(U[:, :d], dtype=torch.float32),
+                                           torch.tensor(V[:, :d], dtype=torch.float32),
+                                           np.sqrt(n * m) / (2.0 * np.sqrt(d)))
     return generate_low_rank_gpu(n, m, d, device=device)
 
 
@@ -198,7 +201,8 @@ def generate_low_rank_gpu(n, m, d, device="cpu", seed=None, force_factored=False
     if force_factored or n * m > _cfg.DENSE_X_MAX_ELEMS:
         return _GroundTruth(A=A, B=B, scale=scale, device=dev)
     X = (A @ B.T) * scale
-    return X.to(device) if torch.device(device).type == "cpu" else X
+    X = X.to(device) if torch.device(device).type == "cpu" else X
+    return _GroundTruth.attach_factors(X, A, B, scale)
 
 
 for _name in ("generate_low_rank_matrix", "generate_structured_embeddings", "generate_svd_embeddings",

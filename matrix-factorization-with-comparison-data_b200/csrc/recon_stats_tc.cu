@@ -7,7 +7,7 @@
 //     staging tables, and computes the row / column means of W (a_r = <U_r, vbar>, b_c = <ubar, V_c>);
 //   * the A operand (128 rows of U, split hi / lo on the fly) lives in TENSOR MEMORY, not shared memory: at the
 //     start of a row block the epilogue warps read their rows of U from global memory and write them with
-//     tcgen05.st next to the accumulators (TMEM columns [128, 128 + K) = hi, [128 + KMAX, ...) = lo).  That
+//     tcgen05.st next to the accumulators (TMEM columns [256, 256 + K) = hi, [384, 384 + K) = lo).  That
 //     frees 64 KB of shared memory at K = 64 for a deeper X ring (5 tiles instead of 3: the round-1 profile
 //     showed the X stream starved by a 3-deep ring) and is what makes K = 128 fit at all;
 //   * ONE producer thread per CTA feeds the rest with TMA tensor copies (cp.async.bulk.tensor.2d, 128-byte
@@ -15,7 +15,7 @@
 //     through a separate ring that runs 2-5 tiles ahead (3-6 slots of 32 KB), the matching X tile;
 //   * ONE thread issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory, M = 128, N = 64, K = 8 per
 //     instruction), three MMAs per K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's
-//     sgemm), accumulating in TMEM (2 stages x 64 columns);
+//     sgemm), accumulating in TMEM (4 stages x 64 columns);
 //   * sixteen epilogue warps (TMEM lane quarter = warp id % 4, 16-column quarter = warp id / 4; eight warps
 //     with 32 columns each left the pipeline waiting on the epilogue: 2.5 us per tile against 0.4 for the MMAs) read the
 //     accumulators with tcgen05.ld, the X tile from swizzled shared memory, and fold both into per-row
@@ -33,7 +33,7 @@ constexpr int TM = 128;                 // tile rows  (UMMA M, TMEM lanes)
 constexpr int TN = 64;                  // tile cols  (UMMA N, TMEM columns per stage)
 constexpr int KMAX = 128;               // largest K handled (4 swizzle slabs of B; A = 2 x 128 TMEM columns)
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
-constexpr int NSTAGE = 2;                // TMEM accumulator stages
+constexpr int NSTAGE = 4;                // TMEM accumulator stages (see the note at the MMA issuer)
 constexpr int MAX_BSTAGE = 4;            // shared-memory stages of the B operand (2 - 4, by K)
 constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 16-column quarter of the tile w / 4
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -65,7 +65,7 @@ __host__ __device__ constexpr uint32_t smem_bytes(int nslab, int nbst, int ring)
   return nbst * b_stage_bytes(nslab) + ring * XSLOT_BYTES + (uint32_t)sizeof(Tail) + 1024u;
 }
 // TMEM columns to allocate (power of two >= 32): 2 accumulator stages + hi and lo of the A operand
-__host__ __device__ constexpr uint32_t tmem_cols(int kpad) { return kpad <= 64 ? 256u : 512u; }
+__host__ __device__ constexpr uint32_t tmem_cols(int kpad) { return (NSTAGE * TN + 2 * kpad) <= 256 ? 256u : 512u; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -308,7 +308,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       }
       double acc[6] = {0, 0, 0, 0, 0, 0};
       for (int it = 0; it < ntiles; ++it) {
-        const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
+        const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
         const uint32_t slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
         const int64_t col0 = (ct_begin + it) * TN;
         if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
@@ -398,10 +398,15 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       __syncwarp();
     } else {
       // ================= MMA issuer (one elected thread) =================
+      // FOUR accumulator stages: with two, the issuer could only start tile t+2 after the epilogue had drained tile
+      // t, and the epilogue could only start a tile after its MMAs had completed -- the round-2 profile at K = 64
+      // showed 28 % of all warp samples on the epilogue's mma_done wait while nothing was saturated (DRAM 39 %, tensor
+      // pipe 29 %, issue 45 %) and neither more B stages nor a deeper X ring moved the time.  With four the MMAs run
+      // up to three tiles ahead of the epilogue.
       if (lane == 0) {
         bool ok = mbar_wait(&tl.a_full, item & 1, err);
         for (int it = 0; ok && it < ntiles; ++it) {
-          const uint32_t u = use + it, st = u & 1, ph = (u >> 1) & 1;
+          const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
           const uint32_t bs = u % (uint32_t)nbst, bph = (u / (uint32_t)nbst) & 1;
           if (!mbar_wait(&tl.b_full[bs], bph, err)) break;
           if (u >= NSTAGE && !mbar_wait(&tl.tmem_free[st], ph ^ 1, err)) break;      // TMEM stage drained

@@ -130,8 +130,12 @@ def _svd_error(fs, gt: GroundTruth, alpha, norm_X):
     s2 = _singular_values_lowrank(U, V - V.mean(dim=0, keepdim=True))
     S2 = torch.zeros(k, dtype=torch.float64, device=U.device)
     S2[: min(k, s2.numel())] = s2[:k]
-    if gt.X is None:
-        s1 = _singular_values_lowrank(gt.A * gt.scale, gt.B - gt.B.mean(dim=0, keepdim=True))
+    if gt.X is None or gt.factors is not None:
+        # low-rank ground truth (factored, or a dense X whose generator left its factors): X - rowmean(X) =
+        # scale * A (B - colmean(B))^T, singular values from a dx x dx core (reference: structure.py:1011-1017
+        # runs a full dense SVD here)
+        A, B, scale = (gt.A, gt.B, gt.scale) if gt.X is None else gt.factors
+        s1 = _singular_values_lowrank(A * scale, B - B.mean(dim=0, keepdim=True))
         S1 = torch.zeros(k, dtype=torch.float64, device=U.device)
         S1[: min(k, s1.numel())] = s1[:k]
     else:

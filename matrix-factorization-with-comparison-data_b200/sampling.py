@@ -198,10 +198,11 @@ def svd_top_sets(gt: GroundTruth, rank, top_fraction=0.3):
     """Top users / items by the row norms of U_k S_k and V_k S_k (generation_data.py:149-162).
     The truncated SVD is a library call (the reference uses ARPACK svds)."""
     n, m = gt.shape
-    if gt.X is None:
-        qa, ra = torch.linalg.qr(gt.A.double())
-        qb, rb = torch.linalg.qr(gt.B.double())
-        uc, s, vch = torch.linalg.svd(gt.scale * (ra @ rb.T))
+    if gt.X is None or gt.factors is not None:
+        A, B, scale = (gt.A, gt.B, gt.scale) if gt.X is None else gt.factors
+        qa, ra = torch.linalg.qr(A.double())
+        qb, rb = torch.linalg.qr(B.double())
+        uc, s, vch = torch.linalg.svd(scale * (ra @ rb.T))
         k = min(rank, s.numel())
         user_norms = torch.linalg.norm((qa @ uc[:, :k]) * s[:k], dim=1)
         item_norms = torch.linalg.norm((qb @ vch.T[:, :k]) * s[:k], dim=1)

@@ -50,10 +50,26 @@ class GroundTruth:
             assert self.A.shape[1] == self.B.shape[1]
             self.shape = (self.A.shape[0], self.B.shape[0])
         self.scale = float(scale)
+        self.factors = None       # dense X that is KNOWN to equal scale * A @ B.T: (A, B, scale), see attach_factors
 
     @classmethod
     def wrap(cls, X, device=None):
-        return X if isinstance(X, GroundTruth) else cls(X=X, device=device)
+        if isinstance(X, GroundTruth):
+            return X
+        gt = cls(X=X, device=device)
+        tag = getattr(X, "_mfcd_factors", None)
+        if tag is not None and tag[3] == X._version:          # untouched since the generator made it
+            gt.factors = (tag[0].to(gt.device), tag[1].to(gt.device), float(tag[2]))
+        return gt
+
+    @staticmethod
+    def attach_factors(X, A, B, scale):
+        """Remember, on a dense X produced by a low-rank generator, the factors it was built from
+        (X = scale * A @ B.T).  Consumers that only need spectral information (svd_error_scaled, the SVD
+        sampler's top sets) then work on d x d cores instead of an O(n m min(n, m)) dense SVD.  The tag is ignored
+        as soon as X is modified in place (version counter) and does not survive copies."""
+        X._mfcd_factors = (A.detach(), B.detach(), float(scale), X._version)
+        return X
 
     def xview(self) -> _lib.XView:
         v = _lib.XView()

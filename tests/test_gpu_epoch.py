@@ -43,7 +43,7 @@ def _records(rng, N, n, m):
 
 
 @pytest.mark.parametrize("N,B", [(1, 1), (31, 7), (4096, 512), (100_003, 4096), (70_000, 70_000), (300_000, 300),
-                                 (2_000_000, 1 << 18)])
+                                 (2_000_000, 1 << 18), (500_000, 5000), (650_000, 10_000), (123_457, 1931)])
 @pytest.mark.parametrize("given_pos", [False, True])
 def test_epoch_batches_is_the_stable_multisplit_of_the_oracle(G, N, B, given_pos):
     """Every batch holds exactly the records whose epoch position falls in its range, in store order (so a
