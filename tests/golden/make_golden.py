@@ -227,6 +227,62 @@ def make_samplers():
     print("samplers.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
 
 
+def make_samplers_next():
+    """The next-ring strategies (proximity / top_k / variance, generation_data.py:29-43, 189-224, 87-99) under
+    pinned torch + numpy seeds, on the same X as samplers.npz."""
+    out = {}
+    torch.manual_seed(11)
+    np.random.seed(11)
+    X = R.generate_X(40, 30, 3, "cpu")
+    out["X"] = X.numpy()
+    torch.manual_seed(31); np.random.seed(31)
+    out["proximity_k5"] = np.array(RG.choose_items_by_proximity(X, 200, set(), k=5), np.int64)
+    torch.manual_seed(32); np.random.seed(32)
+    out["top_k_default"] = np.array(RG.choose_items_top_k(X, 150, set()), np.int64)       # k = max(5, int(0.1 m)) = 5
+    torch.manual_seed(33); np.random.seed(33)
+    out["variance"] = np.array(RG.choose_items_by_variance(X, 400, set()), np.int64)
+    out["variance_probs"] = (torch.var(X, dim=0) / torch.var(X, dim=0).sum()).numpy().astype(np.float64)
+    # top_k gives up after 3 x num_triplets attempts: ask for more than the block can hold (40 users x 5 x 4 pairs = 800)
+    torch.manual_seed(34); np.random.seed(34)
+    out["top_k_saturated"] = np.array(RG.choose_items_top_k(X, 790, set()), np.int64)
+    np.savez_compressed(os.path.join(HERE, "samplers_next.npz"), **out)
+    print("samplers_next.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
+def make_c2_steps(steps=2048):
+    """Config 2 of BASELINE.json (1000 x 1000, d = 10, p = 0.5, K = 3, random sampling): the first `steps` optimiser
+    steps of the reference's first epoch -- the batches its DataLoader handed out, the per-step losses and the
+    weights after the last recorded step.  Sized for the persistent small-batch kernel with several CTAs."""
+    n, m, d, p, s, K, seed, lr, wd = 1000, 1000, 10, 0.5, 1.0, 3, 7, 1e-3, 1e-5
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    X = R.generate_X(n, m, d, "cpu")
+    train_loader, val_loader, test_loader = R.split_dataset_from_triplets(X, int(n * m * p / 2), scale=s, K=K)
+    model = R.MatrixFactorization(n, m, d)
+    U0 = model.U.detach().clone().numpy()
+    V0 = model.V.detach().clone().numpy()
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    losses, bu, bi, bj, bz = [], [], [], [], []
+    model.train()
+    for k, (u, i, j, z) in enumerate(train_loader):           # the loop body of structure.py:845-852
+        if k >= steps:
+            break
+        opt.zero_grad()
+        loss = F.binary_cross_entropy(model(u, i, j), z.float())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        bu.append(u.numpy().astype(np.int16)); bi.append(i.numpy().astype(np.int16)); bj.append(j.numpy().astype(np.int16))
+        bz.append(z.numpy().astype(np.uint8))
+    out = dict(n=n, m=m, d=d, p=p, s=s, K=K, seed=seed, lr=lr, wd=wd, steps=len(losses), U0=U0, V0=V0,
+               U_end=model.U.detach().numpy().copy(), V_end=model.V.detach().numpy().copy(),
+               batch_u=np.concatenate(bu), batch_i=np.concatenate(bi), batch_j=np.concatenate(bj),
+               batch_z=np.concatenate(bz), step_losses=np.array(losses, np.float64),
+               n_train_samples=len(train_loader.dataset))
+    np.savez_compressed(os.path.join(HERE, "train_c2_steps.npz"), **out)
+    print("train_c2_steps.npz", len(losses), "steps, first/last loss", losses[0], losses[-1])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     make_train_fixture("train_c1.npz", 100, 100, 2, 0.1, 1.0, 1, False, epochs=3, seed=0)
@@ -235,3 +291,5 @@ if __name__ == "__main__":
     make_train_fixture("train_d64.npz", 96, 80, 64, 0.2, 1.0, 1, False, epochs=1, seed=3)
     make_kat()
     make_samplers()
+    make_samplers_next()
+    make_c2_steps()

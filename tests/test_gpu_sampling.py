@@ -247,3 +247,47 @@ def test_next_ring_strategies(G, strategy):
         assert (tv[:, 1:] < 5).mean() > 0.5
     more = structure.get_triplets_from_X(X, 40, strategy=strategy, exclude=ts)
     assert not ({tuple(r) for r in more.tolist()} & {tuple(r) for r in t.tolist()})
+
+
+def test_next_ring_strategies_against_reference_recorded_outputs(G):
+    """proximity / top_k / variance against what the REFERENCE produced under pinned seeds (samplers_next.npz):
+    every recorded triplet lies inside the candidate structures the GPU samplers draw from (so the lists and the
+    item law are the reference's), and the GPU samplers' own output obeys the same rules and limits."""
+    import structure
+    from mfcd_b200 import sampling
+    from mfcd_b200.store import GroundTruth
+    g = load_golden("samplers_next.npz")
+    X = torch.from_numpy(g["X"])
+    n, m = X.shape
+    gt = GroundTruth.wrap(X)
+    top5 = sampling._topk_lists(gt, 5, True).cpu().numpy()
+    bot5 = sampling._topk_lists(gt, 5, False).cpu().numpy()
+    # --- proximity (k = 5): i in the user's top-5, j in the bottom-5
+    ref = g["proximity_k5"]
+    assert all(i in top5[u] and j in bot5[u] and i != j for u, i, j in ref) and len(set(map(tuple, ref))) == 200
+    ours = np.array(structure.choose_items_by_proximity(X, 200, None, k=5).tolist(), np.int64)
+    assert len(set(map(tuple, ours))) == 200
+    assert all(i in top5[u] and j in bot5[u] and i != j for u, i, j in ours)
+    # every (top, bottom) pair is reachable by both: position histograms inside the lists are flat-ish
+    pos_ref = np.array([list(top5[u]).index(i) for u, i, j in ref]); pos_our = np.array([list(top5[u]).index(i) for u, i, j in ours])
+    assert set(pos_ref) == set(range(5)) == set(pos_our)
+    # --- top_k (default k = max(5, int(0.1 m)) = 5): i != j both in the user's top-5
+    ref = g["top_k_default"]
+    assert all(i in top5[u] and j in top5[u] and i != j for u, i, j in ref)
+    ours = np.array(structure.choose_items_top_k(X, 150, None).tolist(), np.int64)
+    assert len(set(map(tuple, ours))) == 150 and all(i in top5[u] and j in top5[u] and i != j for u, i, j in ours)
+    # the block holds 40 x 5 x 4 = 800 triplets; with 3 x 790 attempts the reference found 753 of them
+    ref_sat = g["top_k_saturated"]
+    ours_sat = structure.choose_items_top_k(X, 790, None)
+    assert len(ref_sat) == 753 and abs(len(ours_sat) - len(ref_sat)) < 40 and len(ours_sat) < 790
+    # --- variance: item pair without replacement from the variance law
+    probs = g["variance_probs"]
+    var = torch.var(gt.dense(), dim=0).double()
+    assert np.abs((var / var.sum()).cpu().numpy() - probs).max() < 1e-6            # same law as the reference's
+    ref = g["variance"]
+    ours = np.array(structure.choose_items_by_variance(X, 400, None).tolist(), np.int64)
+    assert len(set(map(tuple, ours))) == 400 and (ours[:, 1] != ours[:, 2]).all() and (ref[:, 1] != ref[:, 2]).all()
+    hot = np.argsort(-probs)[: m // 3]                                              # the high-variance third of the items
+    share = lambda t: np.isin(t[:, 1:], hot).mean()
+    expect = probs[hot].sum()
+    assert share(ref) > expect * 0.8 and share(ours) > expect * 0.8 and abs(share(ref) - share(ours)) < 0.08

@@ -410,6 +410,43 @@ def test_step_snapshots(G, name):
         assert G.rel(model.V.detach().cpu().numpy(), g[f"V_step{k}"]) < 1e-5
 
 
+def test_config2_recorded_steps_through_the_persistent_epoch_kernel(G):
+    """BASELINE config 2 (1000 x 1000, d = 10, K = 3, batch 64): the first 2048 steps the REFERENCE took
+    (train_c2_steps.npz) replayed as one epoch of the persistent small-batch kernel (several CTAs, one grid barrier
+    per step) -- per-step losses and weights within 1e-5; and the same through the two-launch path."""
+    import ctypes as C
+    from mfcd_b200 import _lib
+    from mfcd_b200.trainer import MatrixFactorization, OptimizerSpec, run_epoch
+    g = load_golden("train_c2_steps.npz")
+    n, m, d, steps = int(g["n"]), int(g["m"]), int(g["d"]), int(g["steps"])
+    store = G.store_from(g["batch_u"].astype(np.int64), g["batch_i"].astype(np.int64), g["batch_j"].astype(np.int64),
+                         g["batch_z"].astype(np.float64))
+    spec = OptimizerSpec.adam(lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    for variant in ("persistent", "per-step launches"):
+        model = MatrixFactorization(n, m, d)
+        with torch.no_grad():
+            model.U.copy_(torch.from_numpy(g["U0"])); model.V.copy_(torch.from_numpy(g["V0"]))
+        fs = model.flat_state(G.DEV)
+        if variant == "persistent":
+            losses = run_epoch(fs, store, None, 64, spec, 1).cpu().numpy()
+        else:                                       # no workspace -> k_det_small + k_adam per step (mfcd_b200.h)
+            from mfcd_b200._lib import lib, check, ptr, current_stream
+            out = torch.zeros(steps, dtype=torch.float32, device=G.DEV)
+            a = _lib.EpochArgs()
+            a.params, a.grads, a.state1, a.state2 = ptr(fs.params), ptr(fs.grads), ptr(fs.state1), ptr(fs.state2)
+            a.n_users, a.n_items, a.d, a.optimizer, a.mode, a.flags = n, m, d, 0, 1, 0
+            a.rec, a.perm, a.n_samples, a.batch_size = ptr(store.rec), None, len(store), 64
+            a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.momentum = spec.lr, 0.9, 0.999, 1e-8, spec.weight_decay, 0.0
+            a.step0, a.step_losses, a.workspace, a.workspace_bytes, a.stream = 0, ptr(out), None, 0, current_stream()
+            check(lib.mfcd_train_epoch(C.byref(a)), "mfcd_train_epoch")
+            fs.step += steps
+            losses = out.cpu().numpy()
+        assert len(losses) == steps and fs.step == steps
+        assert np.abs(losses - g["step_losses"]).max() < 1e-5 * np.abs(g["step_losses"]).max(), variant
+        assert G.rel(model.U.detach().cpu().numpy(), g["U_end"]) < 1e-5, variant
+        assert G.rel(model.V.detach().cpu().numpy(), g["V_end"]) < 1e-5, variant
+
+
 def test_train_model_api_with_recorded_order(G):
     """structure.train_model on loaders: epoch losses (mean of batch means) and validation losses vs the reference.
     The recorded epoch orders are injected through epoch_perm so the same batches are visited."""

@@ -162,3 +162,20 @@ def test_torch_port_replays_the_reference_bit_for_bit(name):
             for b in O.split_batches(g["test_u"], g["test_i"], g["test_j"], g["test_z"], 64)]
     loss, acc = TP.eval_batches(model, test)
     assert loss == pytest.approx(float(g["test_loss"]), rel=1e-12) and acc == pytest.approx(float(g["test_acc"]), abs=1e-12)
+
+
+def test_config2_first_2048_steps():
+    """BASELINE config 2 (1000 x 1000, d = 10, K = 3): the numpy oracle replays the first 2048 optimiser steps the
+    reference recorded (train_c2_steps.npz) -- per-step losses and final weights within 1e-5."""
+    g = load_golden("train_c2_steps.npz")
+    U, V = g["U0"].copy(), g["V0"].copy()
+    steps = int(g["steps"])
+    bu, bi, bj, bz = (g["batch_u"].astype(np.int64), g["batch_i"].astype(np.int64), g["batch_j"].astype(np.int64),
+                      g["batch_z"].astype(np.float64))
+    assert len(bu) == steps * 64 and bu.max() < 1000 and set(np.unique(bz)) <= {0.0, 1.0}
+    batches = [(bu[k * 64:(k + 1) * 64], bi[k * 64:(k + 1) * 64], bj[k * 64:(k + 1) * 64], bz[k * 64:(k + 1) * 64])
+               for k in range(steps)]
+    losses, _ = O.train_steps(U, V, batches, float(g["lr"]), float(g["wd"]))
+    assert np.abs(np.array(losses) - g["step_losses"]).max() < 1e-5 * np.abs(g["step_losses"]).max()
+    assert np.abs(U - g["U_end"]).max() < 1e-5 * np.abs(g["U_end"]).max()
+    assert np.abs(V - g["V_end"]).max() < 1e-5 * np.abs(g["V_end"]).max()
