@@ -261,13 +261,17 @@ int mfcd_train_epoch_workspace(const mfcd_epoch_args* args, size_t* bytes);
 /* ---- K4: evaluation ----------------------------------------------------------
  * evaluate_model (structure.py:896-921) and the validation pass of train_model
  * (:858-868): batch_loss[b] = mean BCE of batch b (batches of batch_size in
- * record order, last one ragged), *correct += #{(p > 0.5) == z}. */
+ * record order, last one ragged), *correct += #{(p > 0.5) == z}.
+ * batch_acc: one ZEROED 64-bit word per batch (scratch).  The per-sample losses are summed there in fixed
+ * point (integer atomics: exact, and independent of launch shape and of whatever else runs on the GPU), then
+ * divided by the batch's sample count and rounded once to fp32 into batch_loss. */
 int mfcd_triplet_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int32_t d,
-                      int64_t batch_size, float* batch_loss, unsigned long long* correct, void* stream);
+                      int64_t batch_size, float* batch_loss, unsigned long long* correct, int64_t* batch_acc,
+                      void* stream);
 /* compute_ground_truth_metrics (structure.py:1100-1127): per-batch mean of
- * (sigmoid(X[u,i]-X[u,j]) - z)^2 (no scale s) and #{(diff > 0) == z}. */
+ * (sigmoid(X[u,i]-X[u,j]) - z)^2 (no scale s) and #{(diff > 0) == z}; batch_acc as above. */
 int mfcd_ground_truth_eval(const mfcd_xview* X, const mfcd_triplet* rec, int64_t N, int64_t batch_size,
-                           float* batch_mse, unsigned long long* correct, void* stream);
+                           float* batch_mse, unsigned long long* correct, int64_t* batch_acc, void* stream);
 /* MatrixFactorization.forward (structure.py:773-795): p[k] = sigmoid(<U_u, V_i - V_j>). */
 int mfcd_triplet_scores(const float* U, const float* V, const int64_t* u, const int64_t* i,
                         const int64_t* j, int64_t N, int32_t d, float* p, void* stream);

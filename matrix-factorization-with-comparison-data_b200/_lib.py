@@ -86,8 +86,8 @@ SIGNATURES = {
                                 F32, F32, F32, F32, I64, C.c_uint32, P, P, P],
     "mfcd_train_epoch": [C.POINTER(EpochArgs)],
     "mfcd_train_epoch_workspace": [C.POINTER(EpochArgs), C.POINTER(SZ)],
-    "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P],
-    "mfcd_ground_truth_eval": [C.POINTER(XView), P, I64, I64, P, P, P],
+    "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P, P],
+    "mfcd_ground_truth_eval": [C.POINTER(XView), P, I64, I64, P, P, P, P],
     "mfcd_triplet_scores": [P, P, P, P, P, I64, I32, P, P],
     "mfcd_sample_random": [I64, I64, I64, U64, U64, P, P],
     "mfcd_sample_margin": [I64, I64, I64, U64, U64, C.POINTER(XView), F32, P, P],

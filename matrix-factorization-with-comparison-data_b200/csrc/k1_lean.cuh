@@ -278,6 +278,293 @@ k_fwd_bwd_lean(const float* __restrict__ U, const float* __restrict__ V, const m
   }
 }
 
+// ===========================================================================================================
+// K1 span: the user-grouped atomic kernel for d >= 64 (LPT 16 or 32), third profile pass (profiles/r02*).
+//
+// k_fwd_bwd_lean spends a third of its 81 warp instructions per triplet on the hot item rows: every triplet does
+// LDS.128 + 4 FADD + STS.128 per hot row, and the lane groups of a warp take turns (one phase per group).  But
+// the gradient a RUN of one user's triplets sends to hot row h is  (sum over the run of +-g) * U_u : a scalar per
+// (run, hot row) times the row the group already holds.  So here
+//   * lane `sub` of a group keeps the scalar weights of hot slots sub, sub + LPT, ... in registers; a triplet costs
+//     two compares + two predicated adds per slot register, no shared-memory traffic at all;
+//   * when the run closes, the group walks the slots with a non-zero weight (one ballot, then ffs) and adds
+//     weight * U_u to its warp's shared image: one LDS/4 FFMA/STS per DISTINCT hot row of the run instead of one per
+//     reference.  The two groups of a warp walk their lists from opposite ends, so they meet on the same row at
+//     most once per flush (then, and only then, they take turns);
+//   * every lane group owns a CONTIGUOUS span of the batch instead of LPT slots of every warp tile, so a run is cut
+//     only at span ends (a few hundred triplets apart): with ~42 triplets per user per batch at config 4 the user
+//     row is read once and its gradient leaves as one reduction per ~42 triplets (it was ~16), and a flush covers
+//     a whole run.
+// Same arithmetic per triplet as the lean kernel (fast sigmoid for g, exact sigmoid/BCE for the reported loss).
+// ===========================================================================================================
+template <int LPT, int NITER>
+__device__ __forceinline__ void span_image_add(uint32_t addr_row, float wv, const Frag<4> (&cu)[NITER]) {
+  constexpr int STEP = LPT * 16;
+#pragma unroll
+  for (int it = 0; it < NITER; ++it) {
+    float4 t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr_row + it * STEP));
+    t.x = fmaf(wv, cu[it].v[0], t.x); t.y = fmaf(wv, cu[it].v[1], t.y);
+    t.z = fmaf(wv, cu[it].v[2], t.z); t.w = fmaf(wv, cu[it].v[3], t.w);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr_row + it * STEP), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  }
+}
+
+// Called by ALL lanes of the warp; `need` is uniform within a lane group.  Adds weight * cu to the rows of the
+// warp's image for which this group holds a non-zero weight, then clears the weights.
+template <int LPT, int NITER>
+__device__ __forceinline__ void span_flush_weights(bool need, float (&w)[32 / LPT], const Frag<4> (&cu)[NITER],
+                                                   uint32_t my_hot, int grp, int lane) {
+  constexpr uint32_t ROWB = 16u * LPT * NITER;
+  if constexpr (LPT == 32) {
+    // one group per warp, every lane owns its 16 bytes of every row: no sharing at all
+    uint32_t rows = __ballot_sync(0xffffffffu, need && w[0] != 0.f);
+    while (rows) {
+      const int h = __ffs(rows) - 1;
+      rows &= rows - 1;
+      const float wv = __shfl_sync(0xffffffffu, w[0], h);
+      span_image_add<LPT, NITER>(my_hot + h * ROWB, wv, cu);
+    }
+    if (need) w[0] = 0.f;
+  } else {
+    static_assert(LPT == 16, "span kernel: LPT 16 or 32");
+    const uint32_t b0 = __ballot_sync(0xffffffffu, need && w[0] != 0.f);     // slots 0..15 of both groups
+    const uint32_t b1 = __ballot_sync(0xffffffffu, need && w[1] != 0.f);     // slots 16..31
+    uint32_t rows0 = (b0 & 0xffffu) | (b1 << 16);                            // group 0's slot set (warp-uniform)
+    uint32_t rows1 = (b0 >> 16) | (b1 & 0xffff0000u);                        // group 1's
+    while (rows0 | rows1) {
+      // group 0 ascends, group 1 descends: the two walks cross on the same row at most once
+      const int h0 = rows0 ? __ffs(rows0) - 1 : 32;
+      const int h1 = rows1 ? 31 - __clz(rows1) : -1;
+      rows0 &= rows0 - 1;
+      if (h1 >= 0) rows1 ^= 1u << h1;
+      const int h = grp ? h1 : h0;
+      const bool act = grp ? (h1 >= 0) : (h0 < 32);
+      const float cand = (h & 16) ? w[1] : w[0];
+      const float wv = __shfl_sync(0xffffffffu, cand, (lane & 16) | (h & 15));
+      const uint32_t addr = my_hot + (uint32_t)(h & 31) * ROWB;
+      if (h0 == h1) {                                    // both groups want the same row: take turns
+        if (grp == 0) span_image_add<LPT, NITER>(addr, wv, cu);
+        __syncwarp();
+        if (grp == 1) span_image_add<LPT, NITER>(addr, wv, cu);
+      } else if (act) {
+        span_image_add<LPT, NITER>(addr, wv, cu);
+      }
+      __syncwarp();                                      // a row may be the other group's next one
+    }
+    if (need) { w[0] = 0.f; w[1] = 0.f; }
+  }
+}
+
+template <int LPT, int NITER, bool HOT>
+__global__ void __launch_bounds__(kLeanBlock, NITER > 2 ? 1 : (NITER == 2 ? 2 : 3))
+k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
+               int64_t start, int64_t B, int64_t span, float inv_batch, float* __restrict__ gU,
+               float* __restrict__ gV, float* __restrict__ loss_out, const int8_t* __restrict__ item_slot,
+               const int32_t* __restrict__ hot_items, int n_hot) {
+  constexpr int VEC = 4;
+  constexpr int D = VEC * LPT * NITER;
+  constexpr uint32_t ROWB = D * 4;
+  constexpr int STEP = LPT * VEC * 4;
+  constexpr int UNR = 2;
+  constexpr int NW = 32 / LPT;                         // hot slots per lane (up to 32 hot rows)
+  constexpr int IMAGES = kLeanBlock / 32;
+  constexpr uint32_t NO_USER = 0xffffffffu;
+  __shared__ float s_red[kLeanBlock / 32];
+  extern __shared__ __align__(16) float s_hot[];       // HOT: [IMAGES][n_hot][D], one image per warp
+  if constexpr (HOT) {
+    for (int e = threadIdx.x; e < IMAGES * n_hot * D; e += kLeanBlock) s_hot[e] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  const int grp = lane / LPT;
+  const uint64_t lane_off = (uint64_t)(sub * (VEC * 4));
+  const char* Ub = reinterpret_cast<const char*>(U);
+  const char* Vb = reinterpret_cast<const char*>(V);
+  char* gUb = reinterpret_cast<char*>(gU);
+  char* gVb = reinterpret_cast<char*>(gV);
+  const uint32_t my_hot = (uint32_t)__cvta_generic_to_shared(s_hot) +
+                          (uint32_t)(threadIdx.x >> 5) * (uint32_t)n_hot * ROWB + sub * (VEC * 4);
+
+  const int64_t gid = (blockIdx.x * (int64_t)kLeanBlock + threadIdx.x) / LPT;
+  const int64_t s0 = gid * span;                       // this group's records: [s0, s0 + span) of the batch
+  const mfcd_triplet* my_rec = rec + start;
+  float loss_acc = 0.f;
+  uint32_t cur_u = NO_USER;                            // the user run in flight, carried over the whole span
+  Frag<VEC> cu[NITER], accU[NITER];
+  float w[NW];
+#pragma unroll
+  for (int it = 0; it < NITER; ++it) { cu[it] = frag_zero<VEC>(); accU[it] = frag_zero<VEC>(); }
+#pragma unroll
+  for (int k = 0; k < NW; ++k) w[k] = 0.f;
+
+  for (int64_t tb = s0; tb < s0 + span; tb += LPT) {
+    const int nvalid = tb >= B ? 0 : ((B - tb) < LPT ? (int)(B - tb) : LPT);
+    if (__all_sync(0xffffffffu, nvalid == 0)) break;
+    int4 r = make_int4(0, 0, 0, 0);
+    int slots = 0xffff;                                // (slot_i & 0xff) | (slot_j & 0xff) << 8, 0xff = cold
+    if (sub < nvalid) {
+      r = __ldg(reinterpret_cast<const int4*>(my_rec) + (tb + sub));
+      if constexpr (HOT)
+        slots = ((int)__ldg(item_slot + r.y) & 0xff) | (((int)__ldg(item_slot + r.z) & 0xff) << 8);
+    }
+    float x_home = 0.f;
+#pragma unroll 1
+    for (int r0 = 0; r0 < LPT; r0 += UNR) {
+      Frag<VEC> uu[UNR][NITER], dv[UNR][NITER];
+      uint32_t tu[UNR], ti[UNR], tj[UNR];
+      int ts[UNR];
+      float tz[UNR];
+      bool fresh[UNR];
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const int e = (lane & ~(LPT - 1)) + r0 + q;    // source lane: slot r0 + q of this group's tile
+        tu[q] = (uint32_t)__shfl_sync(0xffffffffu, r.x, e);
+        ti[q] = (uint32_t)__shfl_sync(0xffffffffu, r.y, e);
+        tj[q] = (uint32_t)__shfl_sync(0xffffffffu, r.z, e);
+        tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
+        ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
+        const uint32_t prev = (q == 0) ? cur_u : tu[q > 0 ? q - 1 : 0];
+        if (r0 + q >= nvalid) tu[q] = prev;            // padding never opens a run
+        fresh[q] = tu[q] != prev;
+        const char* pu = Ub + ((uint64_t)tu[q] * ROWB + lane_off);
+        const char* pi = Vb + ((uint64_t)ti[q] * ROWB + lane_off);
+        const char* pj = Vb + ((uint64_t)tj[q] * ROWB + lane_off);
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          if (fresh[q]) uu[q][it] = ldg_frag<VEC>(reinterpret_cast<const float*>(pu + it * STEP));
+          const Frag<VEC> a = ldg_frag<VEC>(reinterpret_cast<const float*>(pi + it * STEP));
+          const Frag<VEC> b = ldg_frag<VEC>(reinterpret_cast<const float*>(pj + it * STEP));
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) dv[q][it].v[kk] = a.v[kk] - b.v[kk];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UNR; ++q) {
+        const bool ok = r0 + q < nvalid;
+        if constexpr (HOT) {                           // a run closes: its hot-row weights go to the image
+          const bool close = fresh[q] && cur_u != NO_USER;
+          if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, grp, lane);
+        }
+        if (fresh[q]) {
+          if (cur_u != NO_USER) {                      // ... and its user gradient leaves as one reduction per row
+            char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+#pragma unroll
+            for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+          }
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) { accU[it] = frag_zero<VEC>(); cu[it] = uu[q][it]; }
+          cur_u = tu[q];
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it)
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) part = fmaf(cu[it].v[kk], dv[q][it].v[kk], part);
+        const float x = group_sum<LPT>(part, 0xffffffffu);
+        x_home = (sub == r0 + q) ? x : x_home;
+        float g = bce_grad_score_fast(sigmoid_fast(x), tz[q], inv_batch);
+        if (!ok) g = 0.f;
+        const int si = ts[q] & 0xff, sj = ts[q] >> 8;
+        const bool cold_i = !HOT || si == 0xff;
+        const bool cold_j = !HOT || sj == 0xff;
+#pragma unroll
+        for (int it = 0; it < NITER; ++it)
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) accU[it].v[kk] = fmaf(g, dv[q][it].v[kk], accU[it].v[kk]);
+        if constexpr (HOT) {
+#pragma unroll
+          for (int k = 0; k < NW; ++k) {
+            const int s = sub + LPT * k;
+            w[k] += (si == s) ? g : 0.f;
+            w[k] -= (sj == s) ? g : 0.f;
+          }
+        }
+        if (ok && (cold_i || cold_j)) {
+          char* di = gVb + ((uint64_t)ti[q] * ROWB + lane_off);
+          char* dj = gVb + ((uint64_t)tj[q] * ROWB + lane_off);
+          const float ng = -g;
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) {
+            Frag<VEC> b, nb;
+#pragma unroll
+            for (int kk = 0; kk < VEC; ++kk) {
+              b.v[kk] = g * cu[it].v[kk];
+              nb.v[kk] = ng * cu[it].v[kk];
+            }
+            if (cold_i) red_frag<VEC>(reinterpret_cast<float*>(di + it * STEP), b);
+            if (cold_j) red_frag<VEC>(reinterpret_cast<float*>(dj + it * STEP), nb);
+          }
+        }
+      }
+    }
+    // the tile's losses, one triplet per lane (exact sigmoid / BCE: this is the reported number)
+    if (sub < nvalid) loss_acc += bce_ref(sigmoidf_ref(x_home), __int_as_float(r.w));
+  }
+  // the run still open at the end of the span
+  if constexpr (HOT) {
+    const bool close = cur_u != NO_USER;
+    if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, grp, lane);
+  }
+  if (cur_u != NO_USER) {
+    char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+#pragma unroll
+    for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+  }
+
+  if constexpr (HOT) {
+    __syncthreads();
+    const int per_img = n_hot * D;
+    for (int e = threadIdx.x; e < per_img; e += kLeanBlock) {
+      float t = 0.f;
+#pragma unroll 4
+      for (int wi = 0; wi < IMAGES; ++wi) t += s_hot[wi * per_img + e];
+      if (t != 0.f) atomicAdd(gV + (int64_t)__ldg(hot_items + e / D) * D + (e % D), t);
+    }
+  }
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) s_red[threadIdx.x >> 5] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (lane < kLeanBlock / 32) ? s_red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(loss_out, t * inv_batch);
+  }
+}
+
+static inline bool span_enabled() {
+  static const bool on = !(getenv("MFCD_K1_SPAN") && atoi(getenv("MFCD_K1_SPAN")) == 0);
+  return on;
+}
+
+template <int LPT, int NITER, bool HOT>
+static int launch_span_kernel(const float* U, const float* V, const mfcd_triplet* rec, int64_t start, int64_t B,
+                              float inv_batch, float* gU, float* gV, float* loss, const int8_t* item_slot,
+                              const int32_t* hot_items, int n_hot, cudaStream_t st) {
+  auto kern = k_fwd_bwd_span<LPT, NITER, HOT>;
+  constexpr int want = NITER > 2 ? 1 : (NITER == 2 ? 2 : 3);
+  const size_t smem = HOT ? (size_t)(kLeanBlock / 32) * n_hot * (4 * LPT * NITER) * sizeof(float) : 0;
+  int per_sm = want;
+  if (HOT) {
+    if (smem > 40 * 1024)
+      MFCD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fit = (int)((227 * 1024) / (smem + 1024));
+    per_sm = fit < want ? (fit < 1 ? 1 : fit) : want;
+  }
+  static const int min_tiles = getenv("MFCD_K1_SPAN_MIN_TILES") ? atoi(getenv("MFCD_K1_SPAN_MIN_TILES")) : 4;
+  constexpr int groups_per_cta = kLeanBlock / LPT;
+  const int grid = grid_for(B, groups_per_cta * LPT * (min_tiles < 1 ? 1 : min_tiles), per_sm);
+  const int64_t groups = (int64_t)grid * groups_per_cta;
+  int64_t span = (B + groups - 1) / groups;
+  span = (span + LPT - 1) / LPT * LPT;                 // whole tiles of LPT records
+  kern<<<grid, kLeanBlock, smem, st>>>(U, V, rec, start, B, span, inv_batch, gU, gV, loss, item_slot, hot_items, n_hot);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
+}
+
 // shared memory one hot row costs in the lean kernel: an image per lane group, or per warp (SHARE)
 static inline bool lean_share() {
   static const bool on = !(getenv("MFCD_K1_SHARE") && atoi(getenv("MFCD_K1_SHARE")) == 0);
@@ -325,6 +612,14 @@ template <int LPT, int NITER>
 static int launch_lean(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
                        int64_t B, float inv_batch, float* gU, float* gV, float* loss, const int8_t* item_slot,
                        const int32_t* hot_items, int n_hot, bool runs, bool wire, cudaStream_t st) {
+  if constexpr (LPT >= 16) {
+    if (runs && !wire && perm == nullptr && n_hot <= 32 && span_enabled()) {
+      if (n_hot > 0)
+        return launch_span_kernel<LPT, NITER, true>(U, V, rec, start, B, inv_batch, gU, gV, loss, item_slot,
+                                                    hot_items, n_hot, st);
+      return launch_span_kernel<LPT, NITER, false>(U, V, rec, start, B, inv_batch, gU, gV, loss, nullptr, nullptr, 0, st);
+    }
+  }
 #define MFCD_LEAN_GO(HOT, RUNS, SHARE, WIRE)                                                              \
   return launch_lean_kernel<LPT, NITER, HOT, RUNS, SHARE, WIRE>(U, V, rec, perm, start, B, inv_batch, gU, gV, \
                                                                 loss, item_slot, hot_items, n_hot, smem, st)

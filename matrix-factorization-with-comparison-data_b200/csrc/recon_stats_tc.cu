@@ -142,16 +142,53 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// issue the load of 16 consecutive TMEM columns of this thread's lane; the registers are valid after tmem_ld16_wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+// the "+r" operands tie every later use of the registers to this wait (the compiler cannot hoist a use above it)
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+// packed fp32 pairs (FADD2 / FFMA2 on sm_100): the epilogue is issue-bound, two elements per instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -306,47 +343,84 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
         tc_fence_before();
         mbar_arrive(&tl.a_full);
       }
+      // The epilogue is software-pipelined: the accumulators of tile it+1 are requested from tensor memory (and its
+      // barriers waited for) BEFORE the arithmetic of tile it, so the tcgen05.ld latency -- the round-2 profile had
+      // 4.3 long-scoreboard stall cycles per issued instruction with all sixteen warps in the same phase -- hides
+      // behind ~80 packed FP instructions; a stage / ring slot is handed back as soon as its data sits in registers.
       double acc[6] = {0, 0, 0, 0, 0, 0};
-      for (int it = 0; it < ntiles; ++it) {
-        const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
-        const uint32_t slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
-        const int64_t col0 = (ct_begin + it) * TN;
-        if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
-        if (!mbar_wait(&tl.mma_done[st], ph, err)) break;       // accumulators complete
+      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + quarter * 16;
+      const int chunk0 = (quarter & 1) * 4;
+      const uint32_t xoff = (quarter >> 1) * X_BOX_BYTES + (uint32_t)t * (SLAB_K * 4);
+      uint32_t slot = use % (uint32_t)ring, xph = (use / (uint32_t)ring) & 1;   // ring position, advanced per tile
+      const f32x2 a2 = pk2(a_row, a_row), ns2 = pk2(-s, -s);
+      uint32_t wn[16];                                                          // accumulators in flight
+      bool alive = ntiles > 0;
+      if (alive) {
+        alive = mbar_wait(&tl.x_full[slot], xph, err) && mbar_wait(&tl.mma_done[use % NSTAGE], (use / NSTAGE) & 1, err);
         tc_fence_after();
-        // X box (32 columns) that holds this quarter, and the quarter's first 16-byte chunk inside the box row
-        const float* xbox = reinterpret_cast<const float*>(x_base + slot * XSLOT_BYTES + (quarter >> 1) * X_BOX_BYTES) + t * SLAB_K;
-        const int chunk0 = (quarter & 1) * 4;
-        const float* bcol = &tl.b_col[slot][quarter * 16];
-        float sx = 0.f, sxx = 0.f, swm = 0.f, sww = 0.f, sxw = 0.f, see = 0.f;
+        if (alive) tmem_ld16_issue(lane_addr + (use % NSTAGE) * TN, wn);
+      }
+      for (int it = 0; alive && it < ntiles; ++it) {
+        const uint32_t u = use + it, st = u % NSTAGE;
+        const int64_t col0 = (ct_begin + it) * TN;
+        const uint32_t cur_slot = slot;
+        uint32_t w[16];
+        tmem_ld16_wait(wn);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) w[q] = wn[q];
+        // this tile's X quarter and column means: shared memory -> registers
+        const unsigned char* xrow = x_base + cur_slot * XSLOT_BYTES + xoff;
+        const float* bcol = &tl.b_col[cur_slot][quarter * 16];
+        float4 xv[4], bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xv[q] = *reinterpret_cast<const float4*>(xrow + (((chunk0 + q) ^ sw) << 4));   // un-swizzle the 16-byte chunk
+          bv[q] = *reinterpret_cast<const float4*>(bcol + 4 * q);
+        }
+        // everything of this tile is in registers: hand the accumulator stage and the ring slot back
+        tc_fence_before();
+        mbar_arrive(&tl.x_free[cur_slot]);
+        mbar_arrive(&tl.tmem_free[st]);
+        if (++slot == (uint32_t)ring) { slot = 0; xph ^= 1; }
+        if (it + 1 < ntiles) {                               // request the next tile's accumulators
+          const uint32_t un = u + 1;
+          alive = mbar_wait(&tl.x_full[slot], xph, err) && mbar_wait(&tl.mma_done[un % NSTAGE], (un / NSTAGE) & 1, err);
+          tc_fence_after();
+          if (alive) tmem_ld16_issue(lane_addr + (un % NSTAGE) * TN, wn);
+        }
         const int64_t left = m - (col0 + quarter * 16);
-        const int valid = (int)(left < 16 ? (left < 0 ? 0 : left) : 16);      // columns of this quarter inside X
-        float w[16];
-        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + st * TN + quarter * 16, w);
+        float sx, sxx, swm, sww, sxw, see;
+        if (left >= 16) {                                    // interior tile: packed pairs, no bounds checks
+          f32x2 px = 0, pxx = 0, pwm = 0, pww = 0, pxw = 0, pee = 0;       // (+0.f, +0.f)
 #pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-          const int chunk = chunk0 + (q >> 2);                     // 16-byte chunk inside the box row, un-swizzle
-          const float4 xv = *reinterpret_cast<const float4*>(xbox + ((chunk ^ sw) << 2));
-          const float4 bv = *reinterpret_cast<const float4*>(bcol + q);
-          const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
-          const float bs4[4] = {bv.x, bv.y, bv.z, bv.w};
-          if (valid >= 16) {                                       // interior tile: no per-element bounds checks
+          for (int q = 0; q < 4; ++q) {
+            const f32x2 x01 = pk2(xv[q].x, xv[q].y), x23 = pk2(xv[q].z, xv[q].w);
+            const f32x2 b01 = pk2(bv[q].x, bv[q].y), b23 = pk2(bv[q].z, bv[q].w);
+            const f32x2 w01 = pk2u(w[4 * q], w[4 * q + 1]), w23 = pk2u(w[4 * q + 2], w[4 * q + 3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x = xs4[e];
-              const float wa = w[q + e] - a_row;
-              const float ee = (w[q + e] - bs4[e]) - s * x;
-              sx += x; sxx = fmaf(x, x, sxx);
-              swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
-              see = fmaf(ee, ee, see);
+            for (int h = 0; h < 2; ++h) {
+              const f32x2 x = h ? x23 : x01, b = h ? b23 : b01, wv = h ? w23 : w01;
+              const f32x2 wa = sub2(wv, a2);
+              const f32x2 ee = fma2(ns2, x, sub2(wv, b));                    // (w - b) - s x
+              px = add2(px, x); pxx = fma2(x, x, pxx);
+              pwm = add2(pwm, wa); pww = fma2(wa, wa, pww); pxw = fma2(x, wa, pxw);
+              pee = fma2(ee, ee, pee);
             }
-          } else {
+          }
+          sx = sum2(px); sxx = sum2(pxx); swm = sum2(pwm); sww = sum2(pww); sxw = sum2(pxw); see = sum2(pee);
+        } else {
+          sx = sxx = swm = sww = sxw = see = 0.f;
+          const int valid = (int)(left < 0 ? 0 : left);      // columns of this quarter inside X
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float xs4[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+            const float bs4[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (q + e < valid) {
-                const float x = xs4[e];
-                const float wa = w[q + e] - a_row;
-                const float ee = (w[q + e] - bs4[e]) - s * x;
+              if (4 * q + e < valid) {
+                const float x = xs4[e], wf = __uint_as_float(w[4 * q + e]);
+                const float wa = wf - a_row;
+                const float ee = (wf - bs4[e]) - s * x;
                 sx += x; sxx = fmaf(x, x, sxx);
                 swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
                 see = fmaf(ee, ee, see);
@@ -354,9 +428,6 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tl.x_free[slot]);
-        mbar_arrive(&tl.tmem_free[st]);
         // 16-element fp32 partials, fp64 across tiles
         acc[0] += (double)sx; acc[1] += (double)sxx; acc[2] += (double)swm;
         acc[3] += (double)sww; acc[4] += (double)sxw; acc[5] += (double)see;

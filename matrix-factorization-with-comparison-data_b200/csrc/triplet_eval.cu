@@ -12,55 +12,82 @@ namespace mfcd {
 
 constexpr int kEvalBlock = 256;
 
-// Per-batch loss accumulation that stays accurate for any batch size: a warp keeps a running fp32 sum for the
-// batch it is currently in (tiles are 32 consecutive positions) and issues ONE atomicAdd when the batch index
-// changes -- 64-sample batches cost two atomics, a 4M-sample batch costs one per warp instead of 4M tiny ones.
+// Per-batch loss accumulation that is EXACT and order-independent for any batch size: every sample's loss is
+// converted to 64-bit fixed point (2^-32 units: exact for fp32 values >= 2^-9, absolute error <= 2^-33 below that) and integer sums are associative, so the batch sums do not depend on how the grid, concurrent
+// kernels or the atomics interleave -- a sweep that runs experiments concurrently reports the same bits as the
+// sequential one.  A warp keeps a running sum for the batch it is currently in (tiles are 32 consecutive
+// positions) and issues ONE 64-bit atomic when the batch index changes: 64-sample batches cost two atomics, a
+// 4M-sample batch one per warp.  k_eval_finish turns the sums into fp32 batch means.
+// fixed-point scale: 2^32 for batches of up to 2^24 samples (100 -- the BCE clamp -- * 2^24 * 2^32 < 2^63), one bit
+// less for every doubling of the batch beyond that
+static inline int fix_shift_for(int64_t batch_size) {
+  int shift = 32;
+  for (int64_t cap = int64_t(1) << 24; cap < batch_size && shift > 0; cap <<= 1) --shift;
+  return shift;
+}
 struct BatchAcc {
   int64_t batch;
-  float sum;
+  long long sum;
 };
-__device__ __forceinline__ void batch_acc_flush(BatchAcc& a, float* __restrict__ batch_out, int64_t N,
-                                                int64_t batch_size, int64_t nb, int lane) {
+__device__ __forceinline__ long long to_fix(float v, float scale) { return __float2ll_rn(v * scale); }
+__device__ __forceinline__ long long warp_sum_ll(long long x) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+__device__ __forceinline__ void batch_acc_flush(BatchAcc& a, long long* __restrict__ batch_fix, int lane) {
   if (a.batch >= 0) {
-    const float t = warp_sum(a.sum);
-    if (lane == 0 && t != 0.f) {
-      const int64_t cnt = (a.batch == nb - 1) ? (N - a.batch * batch_size) : batch_size;
-      atomicAdd(batch_out + a.batch, t / (float)cnt);
-    }
+    const long long t = warp_sum_ll(a.sum);
+    if (lane == 0 && t != 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(batch_fix + a.batch), (unsigned long long)t);
   }
   a.batch = -1;
-  a.sum = 0.f;
+  a.sum = 0;
 }
 // adds this lane's value (for position pos, valid or not) to the warp's running batch sum
-__device__ __forceinline__ void batch_acc_add(BatchAcc& a, float v, int64_t pos, bool valid, float* __restrict__ batch_out,
-                                              int64_t N, int64_t batch_size, int64_t nb, int lane) {
+__device__ __forceinline__ void batch_acc_add(BatchAcc& a, float v, int64_t pos, bool valid,
+                                              long long* __restrict__ batch_fix, int64_t batch_size, float scale,
+                                              int lane) {
   const int64_t b = valid ? pos / batch_size : -1;
   const int64_t b0 = __shfl_sync(0xffffffffu, b, 0);
   const bool uniform = __all_sync(0xffffffffu, b == b0 || !valid) && b0 >= 0;
   if (uniform) {                      // the common case: the whole tile lies in one batch
-    if (b0 != a.batch) batch_acc_flush(a, batch_out, N, batch_size, nb, lane), a.batch = b0;
-    a.sum += valid ? v : 0.f;
+    if (b0 != a.batch) batch_acc_flush(a, batch_fix, lane), a.batch = b0;
+    a.sum += valid ? to_fix(v, scale) : 0;
   } else {                            // tile straddles batches (or is the ragged end): per-lane atomics
-    batch_acc_flush(a, batch_out, N, batch_size, nb, lane);
-    if (valid) {
-      const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
-      atomicAdd(batch_out + b, v / (float)cnt);
-    }
+    batch_acc_flush(a, batch_fix, lane);
+    if (valid) atomicAdd(reinterpret_cast<unsigned long long*>(batch_fix + b), (unsigned long long)to_fix(v, scale));
   }
+}
+// batch_out[b] = (sum of batch b) / (its sample count), rounded once to fp32
+__global__ void k_eval_finish(const long long* __restrict__ batch_fix, int64_t N, int64_t batch_size, int64_t nb,
+                              double inv_scale, float* __restrict__ batch_out) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const int64_t cnt = (b == nb - 1) ? (N - b * batch_size) : batch_size;
+  batch_out[b] = (float)((double)batch_fix[b] * inv_scale / (double)cnt);
+}
+static inline int launch_eval_finish(const long long* batch_fix, int64_t N, int64_t batch_size, float* batch_out,
+                                     cudaStream_t st) {
+  const int64_t nb = (N + batch_size - 1) / batch_size;
+  k_eval_finish<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(batch_fix, N, batch_size, nb,
+                                                               1.0 / (double)(int64_t(1) << fix_shift_for(batch_size)), batch_out);
+  MFCD_CHECK_LAUNCH();
+  return MFCD_OK;
 }
 
 template <int VEC, int LPT, int NITER>
 __global__ void __launch_bounds__(kEvalBlock)
 k_eval(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec, int64_t N,
-       int d, int64_t batch_size, float* __restrict__ batch_loss, unsigned long long* __restrict__ correct) {
+       int d, int64_t batch_size, float scale, long long* __restrict__ batch_fix,
+       unsigned long long* __restrict__ correct) {
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const int grp = lane / LPT;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t nb = (N + batch_size - 1) / batch_size;
   unsigned int hits = 0;
-  BatchAcc acc{-1, 0.f};
+  BatchAcc acc{-1, 0};
 
   for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
     const int64_t k = base + lane;
@@ -83,11 +110,11 @@ k_eval(const float* __restrict__ U, const float* __restrict__ V, const mfcd_trip
     const bool valid = lane < nvalid;
     const float z = __int_as_float(r.w);
     const float p = sigmoidf_ref(x_home);
-    batch_acc_add(acc, bce_ref(p, z), k, valid, batch_loss, N, batch_size, nb, lane);
+    batch_acc_add(acc, bce_ref(p, z), k, valid, batch_fix, batch_size, scale, lane);
     const float hard = (p > 0.5f) ? 1.f : 0.f;               // (pred > 0.5).float() == z
     hits += (valid && hard == z) ? 1u : 0u;
   }
-  batch_acc_flush(acc, batch_loss, N, batch_size, nb, lane);
+  batch_acc_flush(acc, batch_fix, lane);
   hits = __reduce_add_sync(0xffffffffu, hits);
   if (lane == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
 }
@@ -95,28 +122,28 @@ k_eval(const float* __restrict__ U, const float* __restrict__ V, const mfcd_trip
 template <int VEC, int LPT, int NITER>
 struct EvalLauncher {
   static int run(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int d, int64_t batch_size,
-                 float* batch_loss, unsigned long long* correct, cudaStream_t st) {
+                 long long* batch_fix, unsigned long long* correct, cudaStream_t st) {
     const int grid = grid_for(N, kEvalBlock, 4);
-    k_eval<VEC, LPT, NITER><<<grid, kEvalBlock, 0, st>>>(U, V, rec, N, d, batch_size, batch_loss, correct);
+    k_eval<VEC, LPT, NITER><<<grid, kEvalBlock, 0, st>>>(
+        U, V, rec, N, d, batch_size, (float)(int64_t(1) << fix_shift_for(batch_size)), batch_fix, correct);
     MFCD_CHECK_LAUNCH();
     return MFCD_OK;
   }
 };
 
 static int launch_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int d,
-                       int64_t batch_size, float* batch_loss, unsigned long long* correct, cudaStream_t st) {
-  MFCD_DISPATCH_ROW_SHAPE(EvalLauncher, d, U, V, rec, N, d, batch_size, batch_loss, correct, st);
+                       int64_t batch_size, long long* batch_fix, unsigned long long* correct, cudaStream_t st) {
+  MFCD_DISPATCH_ROW_SHAPE(EvalLauncher, d, U, V, rec, N, d, batch_size, batch_fix, correct, st);
 }
 
 __global__ void __launch_bounds__(256)
-k_gt_eval(mfcd_xview X, const mfcd_triplet* __restrict__ rec, int64_t N, int64_t batch_size,
-          float* __restrict__ batch_mse, unsigned long long* __restrict__ correct) {
+k_gt_eval(mfcd_xview X, const mfcd_triplet* __restrict__ rec, int64_t N, int64_t batch_size, float scale,
+          long long* __restrict__ batch_fix, unsigned long long* __restrict__ correct) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t nb = (N + batch_size - 1) / batch_size;
   unsigned int hits = 0;
-  BatchAcc acc{-1, 0.f};
+  BatchAcc acc{-1, 0};
   for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
     const int64_t k = base + lane;
     const bool valid = k < N;
@@ -130,9 +157,9 @@ k_gt_eval(mfcd_xview X, const mfcd_triplet* __restrict__ rec, int64_t N, int64_t
       const float hard = (diff > 0.f) ? 1.f : 0.f;
       hits += (hard == z) ? 1u : 0u;
     }
-    batch_acc_add(acc, e2, k, valid, batch_mse, N, batch_size, nb, lane);
+    batch_acc_add(acc, e2, k, valid, batch_fix, batch_size, scale, lane);
   }
-  batch_acc_flush(acc, batch_mse, N, batch_size, nb, lane);
+  batch_acc_flush(acc, batch_fix, lane);
   hits = __reduce_add_sync(0xffffffffu, hits);
   if (lane == 0 && hits) atomicAdd(correct, (unsigned long long)hits);
 }
@@ -196,23 +223,29 @@ static int check_xview(const char* fn, const mfcd_xview* X) {
 
 extern "C" int mfcd_triplet_eval(const float* U, const float* V, const mfcd_triplet* rec, int64_t N, int32_t d,
                                  int64_t batch_size, float* batch_loss, unsigned long long* correct,
-                                 void* stream) {
+                                 int64_t* batch_acc, void* stream) {
   MFCD_REQUIRE(N >= 0 && d >= 1 && batch_size >= 1, "mfcd_triplet_eval: bad sizes");
   if (N == 0) return MFCD_OK;
-  MFCD_REQUIRE(U && V && rec && batch_loss && correct, "mfcd_triplet_eval: NULL pointer");
-  return launch_eval(U, V, rec, N, d, batch_size, batch_loss, correct, as_stream(stream));
+  MFCD_REQUIRE(U && V && rec && batch_loss && correct && batch_acc, "mfcd_triplet_eval: NULL pointer");
+  long long* fix = reinterpret_cast<long long*>(batch_acc);
+  const int rc = launch_eval(U, V, rec, N, d, batch_size, fix, correct, as_stream(stream));
+  if (rc != MFCD_OK) return rc;
+  return launch_eval_finish(fix, N, batch_size, batch_loss, as_stream(stream));
 }
 
 extern "C" int mfcd_ground_truth_eval(const mfcd_xview* X, const mfcd_triplet* rec, int64_t N, int64_t batch_size,
-                                      float* batch_mse, unsigned long long* correct, void* stream) {
+                                      float* batch_mse, unsigned long long* correct, int64_t* batch_acc,
+                                      void* stream) {
   int rc = check_xview("mfcd_ground_truth_eval", X);
   if (rc != MFCD_OK) return rc;
   MFCD_REQUIRE(N >= 0 && batch_size >= 1, "mfcd_ground_truth_eval: bad sizes");
   if (N == 0) return MFCD_OK;
-  MFCD_REQUIRE(rec && batch_mse && correct, "mfcd_ground_truth_eval: NULL pointer");
-  k_gt_eval<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(*X, rec, N, batch_size, batch_mse, correct);
+  MFCD_REQUIRE(rec && batch_mse && correct && batch_acc, "mfcd_ground_truth_eval: NULL pointer");
+  long long* fix = reinterpret_cast<long long*>(batch_acc);
+  k_gt_eval<<<grid_for(N, 256, 8), 256, 0, as_stream(stream)>>>(
+      *X, rec, N, batch_size, (float)(int64_t(1) << fix_shift_for(batch_size)), fix, correct);
   MFCD_CHECK_LAUNCH();
-  return MFCD_OK;
+  return launch_eval_finish(fix, N, batch_size, batch_mse, as_stream(stream));
 }
 
 extern "C" int mfcd_triplet_scores(const float* U, const float* V, const int64_t* u, const int64_t* i,

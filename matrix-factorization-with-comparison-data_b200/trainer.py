@@ -258,10 +258,11 @@ def eval_batches(fs: _FlatState, store: TripletStore, batch_size):
     nb = (N + batch_size - 1) // batch_size
     dev = fs.params.device
     batch_loss = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)
-    correct = torch.zeros(1, dtype=torch.int64, device=dev)
+    acc = torch.zeros(1 + max(nb, 1), dtype=torch.int64, device=dev)    # [#correct | fixed-point batch sums]
+    correct = acc[:1]
     with torch.cuda.device(dev):
         check(lib.mfcd_triplet_eval(ptr(fs.U), ptr(fs.V), ptr(store.rec), N, fs.d, batch_size, ptr(batch_loss),
-                                    ptr(correct), current_stream()), "mfcd_triplet_eval")
+                                    ptr(correct), ptr(acc[1:]), current_stream()), "mfcd_triplet_eval")
     return batch_loss[:nb], correct
 
 
@@ -523,11 +524,12 @@ def compute_ground_truth_metrics(test_loader, X, device, *, world_size=None):
     N = len(loader.store)
     nb = len(loader)
     batch_mse = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)
-    correct = torch.zeros(1, dtype=torch.int64, device=dev)
+    acc = torch.zeros(1 + max(nb, 1), dtype=torch.int64, device=dev)    # [#correct | fixed-point batch sums]
+    correct = acc[:1]
     xv = gt.xview()
     with torch.cuda.device(dev):
         check(lib.mfcd_ground_truth_eval(C.byref(xv), ptr(loader.store.rec), N, loader.batch_size, ptr(batch_mse),
-                                         ptr(correct), current_stream()), "mfcd_ground_truth_eval")
+                                         ptr(correct), ptr(acc[1:]), current_stream()), "mfcd_ground_truth_eval")
     msum, nbs, ncorrect, total = _all_sum([_sum_like_python(batch_mse[:nb]), nb, int(correct.item()), N], dev, world)
     accuracy = ncorrect / total if total > 0 else 0.0
     return msum / nbs, accuracy

@@ -21,6 +21,7 @@ import os
 os.environ.setdefault("OMP_NUM_THREADS", "4")      # the reference pins this at import (structure.py:3)
 
 import itertools
+import types
 import pickle
 
 import numpy as np
@@ -140,6 +141,39 @@ def parameter_scan(n=1000, m=1000, d=2, p=0.5, s=1.0, device='cpu',
     return pending
 
 
+def _adopt_on_stream(obj, stream, seen=None, depth=0):
+    """Tell the caching allocator that every CUDA tensor reachable from ``obj`` is used on ``stream``.
+
+    A repetition is prepared on the caller's stream and finished on a worker stream.  Tensors made during the
+    preparation (ground truth, records, the recorded per-epoch permutations, the tables) belong to the CALLER's
+    stream pool: when the worker drops one of them mid-run (a consumed epoch permutation, a re-ordered store), the
+    allocator would hand the block to the next preparation while the worker's kernels are still reading it.
+    ``Tensor.record_stream`` defers that reuse until the worker stream has passed the point of release."""
+    if seen is None:
+        seen = set()
+    if id(obj) in seen or depth > 12:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+        return
+    if obj is None or isinstance(obj, (str, bytes, int, float, bool, complex, np.ndarray, np.generic, torch.device,
+                                       torch.dtype, torch.cuda.Stream, torch.cuda.Event, type, types.ModuleType,
+                                       types.FunctionType, types.MethodType, types.BuiltinFunctionType)):
+        return
+    if isinstance(obj, dict):
+        children = list(obj.keys()) + list(obj.values())
+    elif isinstance(obj, (list, tuple, set, frozenset)) or type(obj).__name__ == "deque":
+        children = list(obj)
+    elif hasattr(obj, "__dict__"):
+        children = list(vars(obj).values())
+    else:
+        return
+    for child in children:
+        _adopt_on_stream(child, stream, seen, depth + 1)
+
+
 def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrency, devices, save_path, save_every):
     """The sweep with up to ``concurrency`` repetitions in flight.
 
@@ -168,6 +202,7 @@ def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrenc
                     streams[dev] = torch.cuda.Stream(device=dev)
                 st = streams[dev]
                 st.wait_event(ready)                       # the preparation ran on the caller's stream
+                _adopt_on_stream(P, st)
                 with torch.cuda.stream(st):
                     values = _finish_rep(P, is_last=is_last, open_browser=open_browser, progress=False)
                     st.synchronize()

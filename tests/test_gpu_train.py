@@ -248,6 +248,37 @@ def test_user_grouped_kernel_matches_oracle(G, d, hot):
     assert G.rel(gU.cpu().numpy(), gUo) < 2e-5 and G.rel(gV.cpu().numpy(), gVo) < 2e-5
 
 
+@pytest.mark.parametrize("d", [64, 128, 256])
+@pytest.mark.parametrize("B", [1, 15, 16, 17, 33, 257, 5000])
+def test_span_kernel_small_and_ragged_batches(G, d, B):
+    """K1 span (user-grouped batches, d >= 64: contiguous spans per lane group, hot-row weights as scalars): batches
+    smaller than a tile / a span, ragged tails, a start offset, every item hot, and one user for the whole batch."""
+    from mfcd_b200._lib import lib, check, ptr, current_stream
+    rng = np.random.default_rng(1000 * d + B)
+    n, m = 23, 40
+    U = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    V = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    for one_user in (False, True):
+        u = np.zeros(B + 3, np.int64) + 7 if one_user else np.sort(rng.integers(0, n, B + 3))
+        i = rng.integers(0, m, B + 3); j = (i + 1 + rng.integers(0, m - 1, B + 3)) % m
+        z = rng.integers(0, 2, B + 3).astype(np.float64)
+        store = G.store_from(u, i, j, z)
+        nh = 16 if d == 128 else (8 if d == 256 else 32)
+        slot = torch.full((m,), -1, dtype=torch.int8, device=G.DEV)
+        items = torch.arange(nh, dtype=torch.int32, device=G.DEV) + 2          # items 2 .. nh+1 are privatised
+        slot[2:2 + nh] = torch.arange(nh, dtype=torch.int8, device=G.DEV)
+        sl = slice(3, 3 + B)
+        lo, gUo, gVo = O.loss_and_grads(U, V, u[sl], i[sl], j[sl], z[sl].astype(np.float32))
+        Ud, Vd = G.dev_f32(U), G.dev_f32(V)
+        for hot in (True, False):
+            gU = torch.zeros_like(Ud); gV = torch.zeros_like(Vd); loss = torch.zeros(1, device=G.DEV)
+            check(lib.mfcd_triplet_fwd_bwd_ex(ptr(Ud), ptr(Vd), ptr(store.rec), None, 3, B, d, 1.0 / B, ptr(gU),
+                                              ptr(gV), ptr(loss), ptr(slot) if hot else None,
+                                              ptr(items) if hot else None, nh if hot else 0, 1, current_stream()), "ex")
+            assert abs(loss.item() - lo) < 2e-5 * abs(lo), (one_user, hot)
+            assert G.rel(gU.cpu().numpy(), gUo) < 2e-5 and G.rel(gV.cpu().numpy(), gVo) < 2e-5, (one_user, hot)
+
+
 def test_deterministic_mode_is_bit_reproducible(G):
     rng = np.random.default_rng(7)
     U, V, u, i, j, z = _random_problem(rng, 500, 64, 64, 20000, hot=True)
@@ -603,8 +634,9 @@ def test_full_size_properties_c4_shape(G):
     assert (a[1] - b[1]).abs().max().item() < 1e-4 * b[1].abs().max().item()
     assert abs(a[2] - b[2]) < 1e-5 * abs(b[2])
     # the loss equals the evaluation kernel's loss over the same records (one batch)
-    bl = torch.zeros(1, device=G.DEV); correct = torch.zeros(1, dtype=torch.int64, device=G.DEV)
-    check(lib.mfcd_triplet_eval(ptr(U), ptr(V), ptr(rec), B, d, B, ptr(bl), ptr(correct), current_stream()), "k4")
+    bl = torch.zeros(1, device=G.DEV); correct = torch.zeros(2, dtype=torch.int64, device=G.DEV)
+    check(lib.mfcd_triplet_eval(ptr(U), ptr(V), ptr(rec), B, d, B, ptr(bl), ptr(correct), ptr(correct[1:]),
+                                current_stream()), "k4")
     assert abs(bl.item() - b[2]) < 1e-4 * abs(b[2])
     # linearity: gradients scale with inv_batch
     gU2 = torch.zeros_like(U); gV2 = torch.zeros_like(V); l2 = torch.zeros(1, device=G.DEV)
