@@ -312,50 +312,60 @@ __device__ __forceinline__ void span_image_add(uint32_t addr_row, float wv, cons
   }
 }
 
-// Called by ALL lanes of the warp; `need` is uniform within a lane group.  Adds weight * cu to the rows of the
-// warp's image for which this group holds a non-zero weight, then clears the weights.
+// rows of a warp's hot image in the span kernel: all 32 slots at LPT = 16 (the flush walks them unconditionally),
+// the privatised rows only at LPT = 32
+template <int LPT>
+__host__ __device__ constexpr int span_image_rows(int n_hot) { return LPT == 16 ? 32 : n_hot; }
+
+// Called by ALL lanes of the warp; `need` is uniform within a lane group.  Adds weight * cu to the warp's image
+// for every slot, then clears the weights.  No search for the non-zero weights: a first version that walked them
+// (ballot + ffs, the two groups from opposite ends, a clash check per step) cost 45 instructions per visited row;
+// this one costs 7 (SHFL, LDS.128, 4 FFMA, STS.128) for each of the 32 slots, once per run of ~42 triplets.
+// LPT = 16: while group 0 is on slot h, group 1 is on slot h ^ 16, so the two never touch the same row at once.
 template <int LPT, int NITER>
 __device__ __forceinline__ void span_flush_weights(bool need, float (&w)[32 / LPT], const Frag<4> (&cu)[NITER],
-                                                   uint32_t my_hot, int grp, int lane) {
+                                                   uint32_t my_hot, int n_hot, int lane) {
   constexpr uint32_t ROWB = 16u * LPT * NITER;
   if constexpr (LPT == 32) {
-    // one group per warp, every lane owns its 16 bytes of every row: no sharing at all
-    uint32_t rows = __ballot_sync(0xffffffffu, need && w[0] != 0.f);
-    while (rows) {
-      const int h = __ffs(rows) - 1;
-      rows &= rows - 1;
+    (void)need;                                          // one group per warp: need is warp-uniform and true
+#pragma unroll 4
+    for (int h = 0; h < n_hot; ++h) {
       const float wv = __shfl_sync(0xffffffffu, w[0], h);
       span_image_add<LPT, NITER>(my_hot + h * ROWB, wv, cu);
     }
-    if (need) w[0] = 0.f;
+    w[0] = 0.f;
   } else {
     static_assert(LPT == 16, "span kernel: LPT 16 or 32");
-    const uint32_t b0 = __ballot_sync(0xffffffffu, need && w[0] != 0.f);     // slots 0..15 of both groups
-    const uint32_t b1 = __ballot_sync(0xffffffffu, need && w[1] != 0.f);     // slots 16..31
-    uint32_t rows0 = (b0 & 0xffffu) | (b1 << 16);                            // group 0's slot set (warp-uniform)
-    uint32_t rows1 = (b0 >> 16) | (b1 & 0xffff0000u);                        // group 1's
-    while (rows0 | rows1) {
-      // group 0 ascends, group 1 descends: the two walks cross on the same row at most once
-      const int h0 = rows0 ? __ffs(rows0) - 1 : 32;
-      const int h1 = rows1 ? 31 - __clz(rows1) : -1;
-      rows0 &= rows0 - 1;
-      if (h1 >= 0) rows1 ^= 1u << h1;
-      const int h = grp ? h1 : h0;
-      const bool act = grp ? (h1 >= 0) : (h0 < 32);
-      const float cand = (h & 16) ? w[1] : w[0];
-      const float wv = __shfl_sync(0xffffffffu, cand, (lane & 16) | (h & 15));
-      const uint32_t addr = my_hot + (uint32_t)(h & 31) * ROWB;
-      if (h0 == h1) {                                    // both groups want the same row: take turns
-        if (grp == 0) span_image_add<LPT, NITER>(addr, wv, cu);
-        __syncwarp();
-        if (grp == 1) span_image_add<LPT, NITER>(addr, wv, cu);
-      } else if (act) {
-        span_image_add<LPT, NITER>(addr, wv, cu);
-      }
-      __syncwarp();                                      // a row may be the other group's next one
+    const bool g1 = (lane & 16) != 0;
+    // group 0 walks slots 0..31, group 1 walks 16..31, 0..15: first its `wa` half, then its `wb` half
+    const float wa = need ? (g1 ? w[1] : w[0]) : 0.f;
+    const float wb = need ? (g1 ? w[0] : w[1]) : 0.f;
+    const uint32_t base_a = my_hot + (g1 ? 16u * ROWB : 0u);
+    const uint32_t base_b = my_hot + (g1 ? 0u : 16u * ROWB);
+    const int src = lane & 16;
+#pragma unroll 4
+    for (int h = 0; h < 16; ++h) {
+      const float wv = __shfl_sync(0xffffffffu, wa, src | h);
+      span_image_add<LPT, NITER>(base_a + h * ROWB, wv, cu);
     }
+    __syncwarp();                                        // the groups swap halves
+#pragma unroll 4
+    for (int h = 0; h < 16; ++h) {
+      const float wv = __shfl_sync(0xffffffffu, wb, src | h);
+      span_image_add<LPT, NITER>(base_b + h * ROWB, wv, cu);
+    }
+    __syncwarp();
     if (need) { w[0] = 0.f; w[1] = 0.f; }
   }
+}
+
+// sigmoid for the gradient: ex2.approx on -x log2(e), rcp.approx (relative error ~1e-6 for |x| < 30; the reported
+// loss uses the exact functions)
+__device__ __forceinline__ float sigmoid_fast2(float x) {
+  float e, p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(1.f + e));
+  return p;
 }
 
 template <int LPT, int NITER, bool HOT>
@@ -373,21 +383,21 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
   constexpr int IMAGES = kLeanBlock / 32;
   constexpr uint32_t NO_USER = 0xffffffffu;
   __shared__ float s_red[kLeanBlock / 32];
-  extern __shared__ __align__(16) float s_hot[];       // HOT: [IMAGES][n_hot][D], one image per warp
+  extern __shared__ __align__(16) float s_hot[];       // HOT: [IMAGES][img_rows][D], one image per warp
+  const int img_rows = span_image_rows<LPT>(n_hot);
   if constexpr (HOT) {
-    for (int e = threadIdx.x; e < IMAGES * n_hot * D; e += kLeanBlock) s_hot[e] = 0.f;
+    for (int e = threadIdx.x; e < IMAGES * img_rows * D; e += kLeanBlock) s_hot[e] = 0.f;
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPT;
-  const int grp = lane / LPT;
-  const uint64_t lane_off = (uint64_t)(sub * (VEC * 4));
-  const char* Ub = reinterpret_cast<const char*>(U);
-  const char* Vb = reinterpret_cast<const char*>(V);
-  char* gUb = reinterpret_cast<char*>(gU);
-  char* gVb = reinterpret_cast<char*>(gV);
+  // per-lane table bases: a row address is ONE 64-bit multiply-add (index * ROWB + base)
+  const char* Ul = reinterpret_cast<const char*>(U) + sub * (VEC * 4);
+  const char* Vl = reinterpret_cast<const char*>(V) + sub * (VEC * 4);
+  char* gUl = reinterpret_cast<char*>(gU) + sub * (VEC * 4);
+  char* gVl = reinterpret_cast<char*>(gV) + sub * (VEC * 4);
   const uint32_t my_hot = (uint32_t)__cvta_generic_to_shared(s_hot) +
-                          (uint32_t)(threadIdx.x >> 5) * (uint32_t)n_hot * ROWB + sub * (VEC * 4);
+                          (uint32_t)(threadIdx.x >> 5) * (uint32_t)img_rows * ROWB + sub * (VEC * 4);
 
   const int64_t gid = (blockIdx.x * (int64_t)kLeanBlock + threadIdx.x) / LPT;
   const int64_t s0 = gid * span;                       // this group's records: [s0, s0 + span) of the batch
@@ -410,6 +420,8 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
       r = __ldg(reinterpret_cast<const int4*>(my_rec) + (tb + sub));
       if constexpr (HOT)
         slots = ((int)__ldg(item_slot + r.y) & 0xff) | (((int)__ldg(item_slot + r.z) & 0xff) << 8);
+    } else {
+      r.x = (int)NO_USER;                              // padding: continues whatever run is open (see below)
     }
     float x_home = 0.f;
 #pragma unroll 1
@@ -428,14 +440,17 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
         tz[q] = __int_as_float(__shfl_sync(0xffffffffu, r.w, e));
         ts[q] = HOT ? __shfl_sync(0xffffffffu, slots, e) : 0xffff;
         const uint32_t prev = (q == 0) ? cur_u : tu[q > 0 ? q - 1 : 0];
-        if (r0 + q >= nvalid) tu[q] = prev;            // padding never opens a run
+        if (tu[q] == NO_USER) tu[q] = prev;            // padding never opens a run
         fresh[q] = tu[q] != prev;
-        const char* pu = Ub + ((uint64_t)tu[q] * ROWB + lane_off);
-        const char* pi = Vb + ((uint64_t)ti[q] * ROWB + lane_off);
-        const char* pj = Vb + ((uint64_t)tj[q] * ROWB + lane_off);
+        const char* pi = Vl + (uint64_t)ti[q] * ROWB;
+        const char* pj = Vl + (uint64_t)tj[q] * ROWB;
+        if (fresh[q]) {
+          const char* pu = Ul + (uint64_t)tu[q] * ROWB;
+#pragma unroll
+          for (int it = 0; it < NITER; ++it) uu[q][it] = ldg_frag<VEC>(reinterpret_cast<const float*>(pu + it * STEP));
+        }
 #pragma unroll
         for (int it = 0; it < NITER; ++it) {
-          if (fresh[q]) uu[q][it] = ldg_frag<VEC>(reinterpret_cast<const float*>(pu + it * STEP));
           const Frag<VEC> a = ldg_frag<VEC>(reinterpret_cast<const float*>(pi + it * STEP));
           const Frag<VEC> b = ldg_frag<VEC>(reinterpret_cast<const float*>(pj + it * STEP));
 #pragma unroll
@@ -447,11 +462,11 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
         const bool ok = r0 + q < nvalid;
         if constexpr (HOT) {                           // a run closes: its hot-row weights go to the image
           const bool close = fresh[q] && cur_u != NO_USER;
-          if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, grp, lane);
+          if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, n_hot, lane);
         }
         if (fresh[q]) {
           if (cur_u != NO_USER) {                      // ... and its user gradient leaves as one reduction per row
-            char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+            char* du = gUl + (uint64_t)cur_u * ROWB;
 #pragma unroll
             for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
           }
@@ -466,7 +481,13 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
           for (int kk = 0; kk < VEC; ++kk) part = fmaf(cu[it].v[kk], dv[q][it].v[kk], part);
         const float x = group_sum<LPT>(part, 0xffffffffu);
         x_home = (sub == r0 + q) ? x : x_home;
-        float g = bce_grad_score_fast(sigmoid_fast(x), tz[q], inv_batch);
+        const float p = sigmoid_fast2(x);
+        float g = inv_batch * (p - tz[q]);
+        if (fabsf(x) > 27.f) {                         // p(1-p) may be below the reference's 1e-12 clamp: rare
+          const float omp = 1.f - p, qq = omp * p;
+          if (qq < 1e-12f) g = g * 1e12f * omp * p;
+          asm volatile("" ::: "memory");               // keep this a branch, not five predicated instructions
+        }
         if (!ok) g = 0.f;
         const int si = ts[q] & 0xff, sj = ts[q] >> 8;
         const bool cold_i = !HOT || si == 0xff;
@@ -479,13 +500,11 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
 #pragma unroll
           for (int k = 0; k < NW; ++k) {
             const int s = sub + LPT * k;
-            w[k] += (si == s) ? g : 0.f;
-            w[k] -= (sj == s) ? g : 0.f;
+            if (si == s) w[k] += g;
+            if (sj == s) w[k] -= g;
           }
         }
         if (ok && (cold_i || cold_j)) {
-          char* di = gVb + ((uint64_t)ti[q] * ROWB + lane_off);
-          char* dj = gVb + ((uint64_t)tj[q] * ROWB + lane_off);
           const float ng = -g;
 #pragma unroll
           for (int it = 0; it < NITER; ++it) {
@@ -495,8 +514,8 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
               b.v[kk] = g * cu[it].v[kk];
               nb.v[kk] = ng * cu[it].v[kk];
             }
-            if (cold_i) red_frag<VEC>(reinterpret_cast<float*>(di + it * STEP), b);
-            if (cold_j) red_frag<VEC>(reinterpret_cast<float*>(dj + it * STEP), nb);
+            if (cold_i) red_frag<VEC>(reinterpret_cast<float*>(gVl + (uint64_t)ti[q] * ROWB + it * STEP), b);
+            if (cold_j) red_frag<VEC>(reinterpret_cast<float*>(gVl + (uint64_t)tj[q] * ROWB + it * STEP), nb);
           }
         }
       }
@@ -507,18 +526,18 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
   // the run still open at the end of the span
   if constexpr (HOT) {
     const bool close = cur_u != NO_USER;
-    if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, grp, lane);
+    if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, n_hot, lane);
   }
   if (cur_u != NO_USER) {
-    char* du = gUb + ((uint64_t)cur_u * ROWB + lane_off);
+    char* du = gUl + (uint64_t)cur_u * ROWB;
 #pragma unroll
     for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
   }
 
   if constexpr (HOT) {
     __syncthreads();
-    const int per_img = n_hot * D;
-    for (int e = threadIdx.x; e < per_img; e += kLeanBlock) {
+    const int per_img = img_rows * D;
+    for (int e = threadIdx.x; e < n_hot * D; e += kLeanBlock) {
       float t = 0.f;
 #pragma unroll 4
       for (int wi = 0; wi < IMAGES; ++wi) t += s_hot[wi * per_img + e];
@@ -546,7 +565,7 @@ static int launch_span_kernel(const float* U, const float* V, const mfcd_triplet
                               const int32_t* hot_items, int n_hot, cudaStream_t st) {
   auto kern = k_fwd_bwd_span<LPT, NITER, HOT>;
   constexpr int want = NITER > 2 ? 1 : (NITER == 2 ? 2 : 3);
-  const size_t smem = HOT ? (size_t)(kLeanBlock / 32) * n_hot * (4 * LPT * NITER) * sizeof(float) : 0;
+  const size_t smem = HOT ? (size_t)(kLeanBlock / 32) * span_image_rows<LPT>(n_hot) * (4 * LPT * NITER) * sizeof(float) : 0;
   int per_sm = want;
   if (HOT) {
     if (smem > 40 * 1024)

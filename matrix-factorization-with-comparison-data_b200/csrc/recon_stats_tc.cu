@@ -108,6 +108,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas knows the region that follows runs in a
+// single thread, so the uniform-datapath operands of UTCHMMA / UTMALDG need no per-instruction election loop
+// (the round-2 profile showed ~40 scalar instructions and ~130 cycles around every tcgen05.mma: the ISSUER, not the
+// tensor pipe -- 26 % busy -- set the 3 165-cycle tile period at K = 64, four times the MMA floor)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -439,7 +448,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       }
     } else if (warp == PRODUCER_WARP) {
       // ================= TMA producer (one elected thread) =================
-      if (lane == 0) {
+      if (elect_one()) {
         bool ok = true;
         auto issue_x = [&](int it) {
           const uint32_t u = use + it, slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
@@ -474,7 +483,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       // showed 28 % of all warp samples on the epilogue's mma_done wait while nothing was saturated (DRAM 39 %, tensor
       // pipe 29 %, issue 45 %) and neither more B stages nor a deeper X ring moved the time.  With four the MMAs run
       // up to three tiles ahead of the epilogue.
-      if (lane == 0) {
+      if (elect_one()) {
         bool ok = mbar_wait(&tl.a_full, item & 1, err);
         for (int it = 0; ok && it < ntiles; ++it) {
           const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
@@ -484,17 +493,19 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + st * TN;
           const uint32_t bh = smem_u32(b_base + bs * b_stage_bytes(nslab));
-          const uint32_t bl = bh + nslab * B_SLAB_BYTES;
+          // descriptors of the stage's first K step; a K step advances 32 bytes inside a 128-byte swizzle row
+          // (2 units of 16 bytes in the address field), a slab advances B_SLAB_BYTES
+          const uint64_t desc_hi = make_desc(bh);
+          const uint64_t desc_lo = make_desc(bh + nslab * B_SLAB_BYTES);
           uint32_t accumulate = 0;
+#pragma unroll 4
           for (int ks = 0; ks < (kp >> 3); ++ks) {
-            const uint32_t slab = ks >> 2, within = (ks & 3) * 32;     // 8 tf32 = 32 bytes of B = 8 TMEM columns of A per K step
-            const uint32_t t_a_hi = tmem_base + TMEM_A_HI + ks * 8;
+            const uint64_t off = (uint64_t)((ks >> 2) * (B_SLAB_BYTES >> 4) + (ks & 3) * 2);
+            const uint32_t t_a_hi = tmem_base + TMEM_A_HI + ks * 8;      // 8 tf32 = 8 TMEM columns of A per K step
             const uint32_t t_a_lo = tmem_base + TMEM_A_LO + ks * 8;
-            const uint64_t d_b_hi = make_desc(bh + slab * B_SLAB_BYTES + within);
-            const uint64_t d_b_lo = make_desc(bl + slab * B_SLAB_BYTES + within);
-            umma_tf32_ts(d_tmem, t_a_hi, d_b_hi, idesc, accumulate);
-            umma_tf32_ts(d_tmem, t_a_hi, d_b_lo, idesc, 1u);
-            umma_tf32_ts(d_tmem, t_a_lo, d_b_hi, idesc, 1u);
+            umma_tf32_ts(d_tmem, t_a_hi, desc_hi + off, idesc, accumulate);
+            umma_tf32_ts(d_tmem, t_a_hi, desc_lo + off, idesc, 1u);
+            umma_tf32_ts(d_tmem, t_a_lo, desc_hi + off, idesc, 1u);
             accumulate = 1u;
           }
           umma_commit(&tl.b_free[bs]);     // both arrive when the MMAs above have finished (implies fence::before_thread_sync):

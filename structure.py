@@ -21,6 +21,7 @@ import os
 os.environ.setdefault("OMP_NUM_THREADS", "4")      # the reference pins this at import (structure.py:3)
 
 import itertools
+import time
 import types
 import pickle
 
@@ -193,8 +194,12 @@ def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrenc
         devs = [torch.device(x) for x in devices]
     slots = threading.Semaphore(concurrency)
     local = threading.local()
+    trace = [] if os.environ.get("MFCD_SWEEP_TRACE") else None        # (what, unit, thread, t0, t1) wall-clock events
+    global _PHASE_TRACE
+    _PHASE_TRACE = [] if trace is not None else None
 
-    def work(P, dev, ready, is_last):
+    def work(P, dev, ready, is_last, unit_id=0):
+        t_begin = time.perf_counter()
         try:
             with torch.cuda.device(dev):
                 streams = local.__dict__.setdefault("streams", {})
@@ -208,6 +213,8 @@ def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrenc
                     st.synchronize()
                 return values
         finally:
+            if trace is not None:
+                trace.append(("finish", unit_id, threading.get_ident(), t_begin, time.perf_counter()))
             slots.release()
 
     jobs = []                                              # (cfg, [future per repetition])
@@ -238,9 +245,11 @@ def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrenc
             print(f"\nRunning experiment with parameters: {cfg}")
             futs = []
             for rep in range(cfg['reps']):
+                t_wait = time.perf_counter()
                 slots.acquire()
                 dev = devs[unit % len(devs)]
                 unit += 1
+                t_prep = time.perf_counter()
                 try:
                     with torch.cuda.device(dev):
                         dev_arg = device if len(devs) == 1 else dev
@@ -253,10 +262,18 @@ def _scan_concurrent(configs, device, open_browser, batch_size, mode, concurrenc
                 except BaseException:
                     slots.release()
                     raise
-                futs.append(pool.submit(work, P, dev, ready, rep == cfg['reps'] - 1))
+                if trace is not None:
+                    trace.append(("wait_slot", unit, 0, t_wait, t_prep))
+                    trace.append(("prepare", unit, 0, t_prep, time.perf_counter()))
+                futs.append(pool.submit(work, P, dev, ready, rep == cfg['reps'] - 1, unit))
             jobs.append((cfg, futs))
             flush(block=False)
         flush(block=True)
+    if trace is not None:
+        import json
+        with open(os.environ["MFCD_SWEEP_TRACE"], "w") as f:
+            json.dump({"units": sorted(trace, key=lambda e: e[3]), "phases": sorted(_PHASE_TRACE, key=lambda e: e[2])}, f)
+        _PHASE_TRACE = None
     if save_path and pending:
         _append_pickle(save_path, pending)
         pending = []
@@ -327,19 +344,39 @@ def _prepare_rep(n, m, d, p, s, device, lr, weight_decay, num_epochs, K, strateg
     return P
 
 
+_PHASE_TRACE = None        # list: (phase, thread id, t0, t1) of every _finish_rep phase, when a sweep trace is on
+
+
+class _phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.t0 = time.perf_counter() if _PHASE_TRACE is not None else 0.0
+
+    def __exit__(self, *exc):
+        if _PHASE_TRACE is not None:
+            import threading
+            _PHASE_TRACE.append((self.name, threading.get_ident(), self.t0, time.perf_counter()))
+        return False
+
+
 def _finish_rep(P, is_last=False, open_browser=False, progress=True):
     """Train, evaluate and measure one prepared repetition (structure.py:368-409) -> {result key: value}."""
     X, s, device, model, world = P["X"], P["s"], P["device"], P["model"], P["world"]
     train_loader, val_loader, test_loader = P["loaders"]
-    t_losses, v_losses = _trainer.train_model(
-        model, train_loader, val_loader, P["optimizer"], device, num_epochs=P["num_epochs"], is_last=is_last,
-        open_browser=open_browser, mode=_cfg.SCATTER_MODE if P["mode"] is None else P["mode"], progress=progress,
-        world_size=world)
-    test_loss, test_acc = evaluate_model(model, test_loader, device, world_size=world)
-    rec_error = compute_reconstruction_error(model, X, s, world_size=world)
-    (alpha_val, norm_X_val, norm_ratio_val, rec_scaled, pearson_mean, pearson_std, spearman_mean,
-     spearman_std, svd_err, slopes, correlations, spearman_scores, rec_scaled_per_row,
-     alpha_per_row) = compute_alpha_and_norm_ratios(model, X, world_size=world)
+    with _phase("train_model"):
+        t_losses, v_losses = _trainer.train_model(
+            model, train_loader, val_loader, P["optimizer"], device, num_epochs=P["num_epochs"], is_last=is_last,
+            open_browser=open_browser, mode=_cfg.SCATTER_MODE if P["mode"] is None else P["mode"], progress=progress,
+            world_size=world)
+    with _phase("evaluate_model"):
+        test_loss, test_acc = evaluate_model(model, test_loader, device, world_size=world)
+        rec_error = compute_reconstruction_error(model, X, s, world_size=world)
+    with _phase("compute_alpha_and_norm_ratios"):
+        (alpha_val, norm_X_val, norm_ratio_val, rec_scaled, pearson_mean, pearson_std, spearman_mean,
+         spearman_std, svd_err, slopes, correlations, spearman_scores, rec_scaled_per_row,
+         alpha_per_row) = compute_alpha_and_norm_ratios(model, X, world_size=world)
     rand_indices = P["rand_indices"]
     if rand_indices is None:
         rand_indices = torch.randperm(X.shape[0])[:2]                     # structure.py:390

@@ -42,9 +42,25 @@ t_seq, r_seq = run(None)
 units = len(r_seq) * a.reps
 out = {"grid": {k: v for k, v in grid.items()}, "experiments": len(r_seq), "repetitions": units,
        "sequential_s": t_seq, "per_repetition_s": t_seq / units, "concurrent": {}}
+def trace_summary(path):
+    """where the wall time of a concurrent sweep goes: the caller's preparation, and the workers' phases"""
+    tr = json.load(open(path))
+    agg = {}
+    for what, _unit, _thr, t0, t1 in tr["units"]:
+        agg.setdefault(what, []).append(t1 - t0)
+    for what, _thr, t0, t1 in tr["phases"]:
+        agg.setdefault("phase:" + what, []).append(t1 - t0)
+    return {k: {"count": len(v), "total_s": sum(v), "mean_s": sum(v) / len(v)} for k, v in agg.items()}
+
+
 for c in [int(x) for x in a.concurrency.split(",")]:
+    trace_path = os.path.join(ROOT, "gpurun_out", f"sweep_trace_c{c}.json")
+    os.makedirs(os.path.dirname(trace_path), exist_ok=True)
+    os.environ["MFCD_SWEEP_TRACE"] = trace_path
     t, r = run(c)
-    out["concurrent"][str(c)] = {"wall_s": t, "speedup": t_seq / t, "identical_to_sequential": same(r, r_seq)}
+    del os.environ["MFCD_SWEEP_TRACE"]
+    out["concurrent"][str(c)] = {"wall_s": t, "speedup": t_seq / t, "identical_to_sequential": same(r, r_seq),
+                                 "where": trace_summary(trace_path)}
 if a.devices:
     t, r = run(8 * torch.cuda.device_count(), devices="all")
     out["all_gpus"] = {"gpus": torch.cuda.device_count(), "wall_s": t, "speedup": t_seq / t, "identical_to_sequential": same(r, r_seq)}
