@@ -297,20 +297,9 @@ k_fwd_bwd_lean(const float* __restrict__ U, const float* __restrict__ V, const m
 //     a whole run.
 // Same arithmetic per triplet as the lean kernel (fast sigmoid for g, exact sigmoid/BCE for the reported loss).
 // ===========================================================================================================
+struct Frag2;
 template <int LPT, int NITER>
-__device__ __forceinline__ void span_image_add(uint32_t addr_row, float wv, const Frag<4> (&cu)[NITER]) {
-  constexpr int STEP = LPT * 16;
-#pragma unroll
-  for (int it = 0; it < NITER; ++it) {
-    float4 t;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr_row + it * STEP));
-    t.x = fmaf(wv, cu[it].v[0], t.x); t.y = fmaf(wv, cu[it].v[1], t.y);
-    t.z = fmaf(wv, cu[it].v[2], t.z); t.w = fmaf(wv, cu[it].v[3], t.w);
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                 ::"r"(addr_row + it * STEP), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
-  }
-}
+__device__ __forceinline__ void span_image_add(uint32_t addr_row, float wv, const Frag2 (&cu)[NITER]);
 
 // rows of a warp's hot image in the span kernel: all 32 slots at LPT = 16 (the flush walks them unconditionally),
 // the privatised rows only at LPT = 32
@@ -323,7 +312,7 @@ __host__ __device__ constexpr int span_image_rows(int n_hot) { return LPT == 16 
 // this one costs 7 (SHFL, LDS.128, 4 FFMA, STS.128) for each of the 32 slots, once per run of ~42 triplets.
 // LPT = 16: while group 0 is on slot h, group 1 is on slot h ^ 16, so the two never touch the same row at once.
 template <int LPT, int NITER>
-__device__ __forceinline__ void span_flush_weights(bool need, float (&w)[32 / LPT], const Frag<4> (&cu)[NITER],
+__device__ __forceinline__ void span_flush_weights(bool need, float (&w)[32 / LPT], const Frag2 (&cu)[NITER],
                                                    uint32_t my_hot, int n_hot, int lane) {
   constexpr uint32_t ROWB = 16u * LPT * NITER;
   if constexpr (LPT == 32) {
@@ -368,6 +357,38 @@ __device__ __forceinline__ float sigmoid_fast2(float x) {
   return p;
 }
 
+// a row fragment as two packed pairs: (x, y) and (z, w) of the lane's float4
+struct Frag2 {
+  f32x2 lo, hi;
+};
+__device__ __forceinline__ Frag2 ldg_frag2(const float4* __restrict__ p) {
+  const float4 t = __ldg(p);
+  Frag2 f;
+  f.lo = pk2(t.x, t.y);
+  f.hi = pk2(t.z, t.w);
+  return f;
+}
+__device__ __forceinline__ void red_frag2(float4* p, const Frag2& f) {
+  float4 t;
+  unpk2(f.lo, t.x, t.y);
+  unpk2(f.hi, t.z, t.w);
+  atomicAdd(p, t);
+}
+
+template <int LPT, int NITER>
+__device__ __forceinline__ void span_image_add(uint32_t addr_row, float wv, const Frag2 (&cu)[NITER]) {
+  constexpr int STEP = LPT * 16;
+  const f32x2 w2 = pk2(wv, wv);
+#pragma unroll
+  for (int it = 0; it < NITER; ++it) {
+    f32x2 lo, hi;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr_row + it * STEP));
+    lo = fma2(w2, cu[it].lo, lo);
+    hi = fma2(w2, cu[it].hi, hi);
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr_row + it * STEP), "l"(lo), "l"(hi) : "memory");
+  }
+}
+
 template <int LPT, int NITER, bool HOT>
 __global__ void __launch_bounds__(kLeanBlock, NITER > 2 ? 1 : (NITER == 2 ? 2 : 3))
 k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const mfcd_triplet* __restrict__ rec,
@@ -377,7 +398,7 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
   constexpr int VEC = 4;
   constexpr int D = VEC * LPT * NITER;
   constexpr uint32_t ROWB = D * 4;
-  constexpr int STEP = LPT * VEC * 4;
+  constexpr uint32_t ROW4 = LPT * NITER;               // float4 fragments per row
   constexpr int UNR = 2;
   constexpr int NW = 32 / LPT;                         // hot slots per lane (up to 32 hot rows)
   constexpr int IMAGES = kLeanBlock / 32;
@@ -390,12 +411,14 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
-  const int sub = lane % LPT;
-  // per-lane table bases: a row address is ONE 64-bit multiply-add (index * ROWB + base)
-  const char* Ul = reinterpret_cast<const char*>(U) + sub * (VEC * 4);
-  const char* Vl = reinterpret_cast<const char*>(V) + sub * (VEC * 4);
-  char* gUl = reinterpret_cast<char*>(gU) + sub * (VEC * 4);
-  char* gVl = reinterpret_cast<char*>(gV) + sub * (VEC * 4);
+  const uint32_t sub = lane % LPT;
+  // tables as arrays of float4 fragments: fragment (row * ROW4 + sub [+ it * LPT]) -- a 32-bit index (the launcher
+  // checks the tables have fewer than 2^32 fragments), so an address is one IMAD + one IMAD.WIDE off the
+  // kernel-parameter base
+  const float4* U4 = reinterpret_cast<const float4*>(U);
+  const float4* V4 = reinterpret_cast<const float4*>(V);
+  float4* gU4 = reinterpret_cast<float4*>(gU);
+  float4* gV4 = reinterpret_cast<float4*>(gV);
   const uint32_t my_hot = (uint32_t)__cvta_generic_to_shared(s_hot) +
                           (uint32_t)(threadIdx.x >> 5) * (uint32_t)img_rows * ROWB + sub * (VEC * 4);
 
@@ -404,10 +427,10 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
   const mfcd_triplet* my_rec = rec + start;
   float loss_acc = 0.f;
   uint32_t cur_u = NO_USER;                            // the user run in flight, carried over the whole span
-  Frag<VEC> cu[NITER], accU[NITER];
+  Frag2 cu[NITER], accU[NITER];
   float w[NW];
 #pragma unroll
-  for (int it = 0; it < NITER; ++it) { cu[it] = frag_zero<VEC>(); accU[it] = frag_zero<VEC>(); }
+  for (int it = 0; it < NITER; ++it) { cu[it].lo = cu[it].hi = 0; accU[it].lo = accU[it].hi = 0; }
 #pragma unroll
   for (int k = 0; k < NW; ++k) w[k] = 0.f;
 
@@ -416,7 +439,7 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
     if (__all_sync(0xffffffffu, nvalid == 0)) break;
     int4 r = make_int4(0, 0, 0, 0);
     int slots = 0xffff;                                // (slot_i & 0xff) | (slot_j & 0xff) << 8, 0xff = cold
-    if (sub < nvalid) {
+    if ((int)sub < nvalid) {
       r = __ldg(reinterpret_cast<const int4*>(my_rec) + (tb + sub));
       if constexpr (HOT)
         slots = ((int)__ldg(item_slot + r.y) & 0xff) | (((int)__ldg(item_slot + r.z) & 0xff) << 8);
@@ -426,7 +449,7 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
     float x_home = 0.f;
 #pragma unroll 1
     for (int r0 = 0; r0 < LPT; r0 += UNR) {
-      Frag<VEC> uu[UNR][NITER], dv[UNR][NITER];
+      Frag2 uu[UNR][NITER], dv[UNR][NITER];
       uint32_t tu[UNR], ti[UNR], tj[UNR];
       int ts[UNR];
       float tz[UNR];
@@ -442,45 +465,48 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
         const uint32_t prev = (q == 0) ? cur_u : tu[q > 0 ? q - 1 : 0];
         if (tu[q] == NO_USER) tu[q] = prev;            // padding never opens a run
         fresh[q] = tu[q] != prev;
-        const char* pi = Vl + (uint64_t)ti[q] * ROWB;
-        const char* pj = Vl + (uint64_t)tj[q] * ROWB;
+        const uint32_t fi = ti[q] * ROW4 + sub, fj = tj[q] * ROW4 + sub;
         if (fresh[q]) {
-          const char* pu = Ul + (uint64_t)tu[q] * ROWB;
+          const uint32_t fu = tu[q] * ROW4 + sub;
 #pragma unroll
-          for (int it = 0; it < NITER; ++it) uu[q][it] = ldg_frag<VEC>(reinterpret_cast<const float*>(pu + it * STEP));
+          for (int it = 0; it < NITER; ++it) uu[q][it] = ldg_frag2(U4 + (fu + it * LPT));
         }
 #pragma unroll
         for (int it = 0; it < NITER; ++it) {
-          const Frag<VEC> a = ldg_frag<VEC>(reinterpret_cast<const float*>(pi + it * STEP));
-          const Frag<VEC> b = ldg_frag<VEC>(reinterpret_cast<const float*>(pj + it * STEP));
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) dv[q][it].v[kk] = a.v[kk] - b.v[kk];
+          const Frag2 a = ldg_frag2(V4 + (fi + it * LPT));
+          const Frag2 b = ldg_frag2(V4 + (fj + it * LPT));
+          dv[q][it].lo = sub2(a.lo, b.lo);
+          dv[q][it].hi = sub2(a.hi, b.hi);
         }
       }
 #pragma unroll
       for (int q = 0; q < UNR; ++q) {
         const bool ok = r0 + q < nvalid;
-        if constexpr (HOT) {                           // a run closes: its hot-row weights go to the image
-          const bool close = fresh[q] && cur_u != NO_USER;
-          if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, n_hot, lane);
-        }
-        if (fresh[q]) {
-          if (cur_u != NO_USER) {                      // ... and its user gradient leaves as one reduction per row
-            char* du = gUl + (uint64_t)cur_u * ROWB;
+        // a run closes (rare: ~1 in 42 triplets per group at config 4): its hot-row weights go to the image, its
+        // user gradient leaves as one reduction per row, the new user's row becomes the current one
+        if (__any_sync(0xffffffffu, fresh[q])) {
+          if constexpr (HOT)
+            span_flush_weights<LPT, NITER>(fresh[q] && cur_u != NO_USER, w, cu, my_hot, n_hot, lane);
+          if (fresh[q]) {
+            if (cur_u != NO_USER) {
+              const uint32_t fu = cur_u * ROW4 + sub;
 #pragma unroll
-            for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+              for (int it = 0; it < NITER; ++it) red_frag2(gU4 + (fu + it * LPT), accU[it]);
+            }
+#pragma unroll
+            for (int it = 0; it < NITER; ++it) { accU[it].lo = accU[it].hi = 0; cu[it] = uu[q][it]; }
+            cur_u = tu[q];
           }
-#pragma unroll
-          for (int it = 0; it < NITER; ++it) { accU[it] = frag_zero<VEC>(); cu[it] = uu[q][it]; }
-          cur_u = tu[q];
         }
-        float part = 0.f;
+        f32x2 part2 = mul2(cu[0].lo, dv[q][0].lo);
+        part2 = fma2(cu[0].hi, dv[q][0].hi, part2);
 #pragma unroll
-        for (int it = 0; it < NITER; ++it)
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) part = fmaf(cu[it].v[kk], dv[q][it].v[kk], part);
-        const float x = group_sum<LPT>(part, 0xffffffffu);
-        x_home = (sub == r0 + q) ? x : x_home;
+        for (int it = 1; it < NITER; ++it) {
+          part2 = fma2(cu[it].lo, dv[q][it].lo, part2);
+          part2 = fma2(cu[it].hi, dv[q][it].hi, part2);
+        }
+        const float x = group_sum<LPT>(sum2(part2), 0xffffffffu);
+        x_home = ((int)sub == r0 + q) ? x : x_home;
         const float p = sigmoid_fast2(x);
         float g = inv_batch * (p - tz[q]);
         if (fabsf(x) > 27.f) {                         // p(1-p) may be below the reference's 1e-12 clamp: rare
@@ -492,36 +518,36 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
         const int si = ts[q] & 0xff, sj = ts[q] >> 8;
         const bool cold_i = !HOT || si == 0xff;
         const bool cold_j = !HOT || sj == 0xff;
+        const f32x2 g2 = pk2(g, g);
 #pragma unroll
-        for (int it = 0; it < NITER; ++it)
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) accU[it].v[kk] = fmaf(g, dv[q][it].v[kk], accU[it].v[kk]);
+        for (int it = 0; it < NITER; ++it) {
+          accU[it].lo = fma2(g2, dv[q][it].lo, accU[it].lo);
+          accU[it].hi = fma2(g2, dv[q][it].hi, accU[it].hi);
+        }
         if constexpr (HOT) {
 #pragma unroll
           for (int k = 0; k < NW; ++k) {
-            const int s = sub + LPT * k;
+            const int s = (int)sub + LPT * k;
             if (si == s) w[k] += g;
             if (sj == s) w[k] -= g;
           }
         }
         if (ok && (cold_i || cold_j)) {
-          const float ng = -g;
+          const f32x2 ng2 = pk2(-g, -g);
+          const uint32_t fi = ti[q] * ROW4 + sub, fj = tj[q] * ROW4 + sub;
 #pragma unroll
           for (int it = 0; it < NITER; ++it) {
-            Frag<VEC> b, nb;
-#pragma unroll
-            for (int kk = 0; kk < VEC; ++kk) {
-              b.v[kk] = g * cu[it].v[kk];
-              nb.v[kk] = ng * cu[it].v[kk];
-            }
-            if (cold_i) red_frag<VEC>(reinterpret_cast<float*>(gVl + (uint64_t)ti[q] * ROWB + it * STEP), b);
-            if (cold_j) red_frag<VEC>(reinterpret_cast<float*>(gVl + (uint64_t)tj[q] * ROWB + it * STEP), nb);
+            Frag2 b, nb;
+            b.lo = mul2(g2, cu[it].lo); b.hi = mul2(g2, cu[it].hi);
+            nb.lo = mul2(ng2, cu[it].lo); nb.hi = mul2(ng2, cu[it].hi);
+            if (cold_i) red_frag2(gV4 + (fi + it * LPT), b);
+            if (cold_j) red_frag2(gV4 + (fj + it * LPT), nb);
           }
         }
       }
     }
     // the tile's losses, one triplet per lane (exact sigmoid / BCE: this is the reported number)
-    if (sub < nvalid) loss_acc += bce_ref(sigmoidf_ref(x_home), __int_as_float(r.w));
+    if ((int)sub < nvalid) loss_acc += bce_ref(sigmoidf_ref(x_home), __int_as_float(r.w));
   }
   // the run still open at the end of the span
   if constexpr (HOT) {
@@ -529,9 +555,9 @@ k_fwd_bwd_span(const float* __restrict__ U, const float* __restrict__ V, const m
     if (__any_sync(0xffffffffu, close)) span_flush_weights<LPT, NITER>(close, w, cu, my_hot, n_hot, lane);
   }
   if (cur_u != NO_USER) {
-    char* du = gUl + (uint64_t)cur_u * ROWB;
+    const uint32_t fu = cur_u * ROW4 + sub;
 #pragma unroll
-    for (int it = 0; it < NITER; ++it) red_frag<VEC>(reinterpret_cast<float*>(du + it * STEP), accU[it]);
+    for (int it = 0; it < NITER; ++it) red_frag2(gU4 + (fu + it * LPT), accU[it]);
   }
 
   if constexpr (HOT) {

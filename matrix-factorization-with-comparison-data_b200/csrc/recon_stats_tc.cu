@@ -16,10 +16,9 @@
 //   * ONE thread issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory, M = 128, N = 64, K = 8 per
 //     instruction), three MMAs per K step (hi.hi + hi.lo + lo.hi: fp32-grade products like the reference's
 //     sgemm), accumulating in TMEM (4 stages x 64 columns);
-//   * sixteen epilogue warps (TMEM lane quarter = warp id % 4, 16-column quarter = warp id / 4; eight warps
-//     with 32 columns each left the pipeline waiting on the epilogue: 2.5 us per tile against 0.4 for the MMAs) read the
-//     accumulators with tcgen05.ld, the X tile from swizzled shared memory, and fold both into per-row
-//     fp64 sums.
+//   * sixteen epilogue warps in two groups of eight that take alternate tiles (TMEM lane quarter = warp id % 4,
+//     32-column half = (warp id / 4) % 2, group = warp id / 8) read the accumulators with tcgen05.ld, the X tile
+//     from swizzled shared memory, and fold both into per-row fp64 sums with packed fp32x2 arithmetic.
 // mbarriers connect the roles; every wait is bounded, so a pipeline bug raises an error flag and lets
 // the kernel drain instead of hanging the GPU.
 #include <cuda.h>
@@ -35,10 +34,10 @@ constexpr int KMAX = 128;               // largest K handled (4 swizzle slabs of
 constexpr int SLAB_K = 32;              // tf32 elements per 128-byte swizzle row
 constexpr int NSTAGE = 4;                // TMEM accumulator stages (see the note at the MMA issuer)
 constexpr int MAX_BSTAGE = 4;            // shared-memory stages of the B operand (2 - 4, by K)
-constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 16-column quarter of the tile w / 4
+constexpr int EPI_WARPS = 16;           // warp w: TMEM lane quarter w % 4, 32-column half (w / 4) % 2, tile group w / 8
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
-constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1, BPRODUCER_WARP = EPI_WARPS + 2;
+constexpr int NTHREADS = (EPI_WARPS + 3) * 32;
 constexpr uint32_t B_SLAB_BYTES = TN * 128;
 constexpr uint32_t TMEM_A_HI = NSTAGE * TN;            // TMEM column of the A operand's hi part
 constexpr uint32_t TMEM_A_LO = TMEM_A_HI + KMAX;       // ... and of its lo part
@@ -167,36 +166,9 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                :: "memory");
 }
 
-// packed fp32 pairs (FADD2 / FFMA2 on sm_100): the epilogue is issue-bound, two elements per instruction
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
 __device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
   f32x2 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ float sum2(f32x2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo + hi;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
   return r;
 }
 
@@ -273,7 +245,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
     tl.error = 0;
     for (int k = 0; k < MAX_RING; ++k) {
       mbar_init(&tl.x_full[k], 1);
-      mbar_init(&tl.x_free[k], EPI_THREADS);
+      mbar_init(&tl.x_free[k], EPI_THREADS / 2);        // one group of eight warps per tile
     }
     for (int st = 0; st < MAX_BSTAGE; ++st) {
       mbar_init(&tl.b_full[st], 1);
@@ -281,7 +253,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
     }
     for (int st = 0; st < NSTAGE; ++st) {
       mbar_init(&tl.mma_done[st], 1);
-      mbar_init(&tl.tmem_free[st], EPI_THREADS);
+      mbar_init(&tl.tmem_free[st], EPI_THREADS / 2);
     }
     mbar_init(&tl.a_full, EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -352,116 +324,126 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
         tc_fence_before();
         mbar_arrive(&tl.a_full);
       }
-      // The epilogue is software-pipelined: the accumulators of tile it+1 are requested from tensor memory (and its
-      // barriers waited for) BEFORE the arithmetic of tile it, so the tcgen05.ld latency -- the round-2 profile had
-      // 4.3 long-scoreboard stall cycles per issued instruction with all sixteen warps in the same phase -- hides
-      // behind ~80 packed FP instructions; a stage / ring slot is handed back as soon as its data sits in registers.
+      // Two groups of eight warps take ALTERNATE tiles (group = warp / 8; inside a group: TMEM lane quarter =
+      // warp % 4, 32-column half of the tile = (warp / 4) % 2).  The round-2 profiles showed the sixteen-warp,
+      // one-tile-at-a-time epilogue as the pipeline's slow stage: ~170 instructions per thread and tile taking
+      // ~1 950 cycles (4 warps per scheduler, all in the same phase of the same tile, long-scoreboard and FP64-pipe
+      // stalls exposed) against 768 cycles of MMAs.  With 32 columns per thread the per-tile overhead (barrier
+      // waits, address arithmetic, the six fp32 -> fp64 folds) is paid once per 32 elements instead of once per 16,
+      // and while one group waits for its accumulators the other one computes.
       double acc[6] = {0, 0, 0, 0, 0, 0};
-      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + quarter * 16;
-      const int chunk0 = (quarter & 1) * 4;
-      const uint32_t xoff = (quarter >> 1) * X_BOX_BYTES + (uint32_t)t * (SLAB_K * 4);
-      uint32_t slot = use % (uint32_t)ring, xph = (use / (uint32_t)ring) & 1;   // ring position, advanced per tile
+      const int half = (warp >> 2) & 1;                         // columns half*32 .. +31 of the tile = X box `half`
+      const int egrp = warp >> 3;                               // this group's tiles: it = egrp, egrp + 2, ...
+      const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + half * 32;
+      const uint32_t xoff = half * X_BOX_BYTES + (uint32_t)t * (SLAB_K * 4);
+      const uint32_t u0 = use + egrp;
+      uint32_t slot = u0 % (uint32_t)ring, xph = (u0 / (uint32_t)ring) & 1;     // ring position, advanced by 2 per tile
       const f32x2 a2 = pk2(a_row, a_row), ns2 = pk2(-s, -s);
-      uint32_t wn[16];                                                          // accumulators in flight
-      bool alive = ntiles > 0;
-      if (alive) {
-        alive = mbar_wait(&tl.x_full[slot], xph, err) && mbar_wait(&tl.mma_done[use % NSTAGE], (use / NSTAGE) & 1, err);
+      for (int it = egrp; it < ntiles; it += 2) {
+        const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
+        const int64_t col0 = (ct_begin + it) * TN + half * 32;
+        if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
+        if (!mbar_wait(&tl.mma_done[st], ph, err)) break;       // accumulators complete
         tc_fence_after();
-        if (alive) tmem_ld16_issue(lane_addr + (use % NSTAGE) * TN, wn);
-      }
-      for (int it = 0; alive && it < ntiles; ++it) {
-        const uint32_t u = use + it, st = u % NSTAGE;
-        const int64_t col0 = (ct_begin + it) * TN;
-        const uint32_t cur_slot = slot;
-        uint32_t w[16];
-        tmem_ld16_wait(wn);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) w[q] = wn[q];
-        // this tile's X quarter and column means: shared memory -> registers
-        const unsigned char* xrow = x_base + cur_slot * XSLOT_BYTES + xoff;
-        const float* bcol = &tl.b_col[cur_slot][quarter * 16];
-        float4 xv[4], bv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          xv[q] = *reinterpret_cast<const float4*>(xrow + (((chunk0 + q) ^ sw) << 4));   // un-swizzle the 16-byte chunk
-          bv[q] = *reinterpret_cast<const float4*>(bcol + 4 * q);
+        uint32_t w[32];
+        {
+          uint32_t (&wa)[16] = *reinterpret_cast<uint32_t (*)[16]>(&w[0]);
+          uint32_t (&wb)[16] = *reinterpret_cast<uint32_t (*)[16]>(&w[16]);
+          tmem_ld16_issue(lane_addr + st * TN, wa);
+          tmem_ld16_issue(lane_addr + st * TN + 16, wb);
+          tmem_ld16_wait(wa);
+          tmem_ld16_wait(wb);
         }
-        // everything of this tile is in registers: hand the accumulator stage and the ring slot back
         tc_fence_before();
-        mbar_arrive(&tl.x_free[cur_slot]);
-        mbar_arrive(&tl.tmem_free[st]);
-        if (++slot == (uint32_t)ring) { slot = 0; xph ^= 1; }
-        if (it + 1 < ntiles) {                               // request the next tile's accumulators
-          const uint32_t un = u + 1;
-          alive = mbar_wait(&tl.x_full[slot], xph, err) && mbar_wait(&tl.mma_done[un % NSTAGE], (un / NSTAGE) & 1, err);
-          tc_fence_after();
-          if (alive) tmem_ld16_issue(lane_addr + (un % NSTAGE) * TN, wn);
-        }
-        const int64_t left = m - (col0 + quarter * 16);
-        float sx, sxx, swm, sww, sxw, see;
-        if (left >= 16) {                                    // interior tile: packed pairs, no bounds checks
-          f32x2 px = 0, pxx = 0, pwm = 0, pww = 0, pxw = 0, pee = 0;       // (+0.f, +0.f)
+        mbar_arrive(&tl.tmem_free[st]);                         // the accumulator stage is in registers
+        const unsigned char* xrow = x_base + slot * XSLOT_BYTES + xoff;
+        const float* bcol = &tl.b_col[slot][half * 32];
+        const int64_t left = m - col0;                          // columns of this half inside X
+        float sx = 0.f, sxx = 0.f, swm = 0.f, sww = 0.f, sxw = 0.f, see = 0.f;
+        f32x2 px = 0, pxx = 0, pwm = 0, pww = 0, pxw = 0, pee = 0;           // (+0.f, +0.f)
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {                        // two passes of 16 columns (register budget)
+          float4 xv[4], bv[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const f32x2 x01 = pk2(xv[q].x, xv[q].y), x23 = pk2(xv[q].z, xv[q].w);
-            const f32x2 b01 = pk2(bv[q].x, bv[q].y), b23 = pk2(bv[q].z, bv[q].w);
-            const f32x2 w01 = pk2u(w[4 * q], w[4 * q + 1]), w23 = pk2u(w[4 * q + 2], w[4 * q + 3]);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const f32x2 x = h ? x23 : x01, b = h ? b23 : b01, wv = h ? w23 : w01;
-              const f32x2 wa = sub2(wv, a2);
-              const f32x2 ee = fma2(ns2, x, sub2(wv, b));                    // (w - b) - s x
-              px = add2(px, x); pxx = fma2(x, x, pxx);
-              pwm = add2(pwm, wa); pww = fma2(wa, wa, pww); pxw = fma2(x, wa, pxw);
-              pee = fma2(ee, ee, pee);
-            }
+            xv[q] = *reinterpret_cast<const float4*>(xrow + (((hq * 4 + q) ^ sw) << 4));   // un-swizzle the 16-byte chunk
+            bv[q] = *reinterpret_cast<const float4*>(bcol + hq * 16 + 4 * q);
           }
-          sx = sum2(px); sxx = sum2(pxx); swm = sum2(pwm); sww = sum2(pww); sxw = sum2(pxw); see = sum2(pee);
-        } else {
-          sx = sxx = swm = sww = sxw = see = 0.f;
-          const int valid = (int)(left < 0 ? 0 : left);      // columns of this quarter inside X
+          if (hq == 1) mbar_arrive(&tl.x_free[slot]);           // the whole X half-row has been read
+          if (left >= 32) {                                     // interior tile: packed pairs, no bounds checks
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float xs4[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
-            const float bs4[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
+            for (int q = 0; q < 4; ++q) {
+              const f32x2 x01 = pk2(xv[q].x, xv[q].y), x23 = pk2(xv[q].z, xv[q].w);
+              const f32x2 b01 = pk2(bv[q].x, bv[q].y), b23 = pk2(bv[q].z, bv[q].w);
+              const int c = hq * 16 + 4 * q;
+              const f32x2 w01 = pk2u(w[c], w[c + 1]), w23 = pk2u(w[c + 2], w[c + 3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (4 * q + e < valid) {
-                const float x = xs4[e], wf = __uint_as_float(w[4 * q + e]);
-                const float wa = wf - a_row;
-                const float ee = (wf - bs4[e]) - s * x;
-                sx += x; sxx = fmaf(x, x, sxx);
-                swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
-                see = fmaf(ee, ee, see);
+              for (int h = 0; h < 2; ++h) {
+                const f32x2 x = h ? x23 : x01, b = h ? b23 : b01, wv = h ? w23 : w01;
+                const f32x2 wa = sub2(wv, a2);
+                const f32x2 ee = fma2(ns2, x, sub2(wv, b));                  // (w - b) - s x
+                px = add2(px, x); pxx = fma2(x, x, pxx);
+                pwm = add2(pwm, wa); pww = fma2(wa, wa, pww); pxw = fma2(x, wa, pxw);
+                pee = fma2(ee, ee, pee);
+              }
+            }
+          } else {
+            const int valid = (int)(left < 0 ? 0 : left);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float xs4[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+              const float bs4[4] = {bv[q].x, bv[q].y, bv[q].z, bv[q].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = hq * 16 + 4 * q + e;
+                if (c < valid) {
+                  const float x = xs4[e], wf = __uint_as_float(w[c]);
+                  const float wa = wf - a_row;
+                  const float ee = (wf - bs4[e]) - s * x;
+                  sx += x; sxx = fmaf(x, x, sxx);
+                  swm += wa; sww = fmaf(wa, wa, sww); sxw = fmaf(x, wa, sxw);
+                  see = fmaf(ee, ee, see);
+                }
               }
             }
           }
         }
-        // 16-element fp32 partials, fp64 across tiles
+        if (left >= 32) {
+          sx = sum2(px); sxx = sum2(pxx); swm = sum2(pwm); sww = sum2(pww); sxw = sum2(pxw); see = sum2(pee);
+        }
+        // 32-element fp32 partials, fp64 across tiles
         acc[0] += (double)sx; acc[1] += (double)sxx; acc[2] += (double)swm;
         acc[3] += (double)sww; acc[4] += (double)sxw; acc[5] += (double)see;
+        slot += 2;
+        if (slot >= (uint32_t)ring) { slot -= (uint32_t)ring; xph ^= 1; }
       }
       if (gr < n) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) atomicAdd(row_stats + gr * 8 + q, acc[q]);
-        if (ct_begin == 0 && quarter == 0) row_stats[gr * 8 + 6] = (double)a_row;
+        if (ct_begin == 0 && warp < 4) row_stats[gr * 8 + 6] = (double)a_row;
       }
     } else if (warp == PRODUCER_WARP) {
-      // ================= TMA producer (one elected thread) =================
+      // ================= TMA producer of the X stream (one elected thread) =================
+      // X and the B operand have their own producer warps: with one thread issuing both, the request for the B
+      // tile of tile t sat behind the wait for a free X ring slot (the ring is full whenever HBM is the limit), so
+      // B ran only ~2 tiles ahead of its MMAs whatever the number of B stages.
       if (elect_one()) {
-        bool ok = true;
-        auto issue_x = [&](int it) {
+        for (int it = 0; it < ntiles; ++it) {
           const uint32_t u = use + it, slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
           const int col0 = (int)((ct_begin + it) * TN);
-          if (u >= (uint32_t)ring && !mbar_wait(&tl.x_free[slot], xph ^ 1, err)) { ok = false; return; }
+          if (u >= (uint32_t)ring && !mbar_wait(&tl.x_free[slot], xph ^ 1, err)) break;
           mbar_arrive_expect_tx(&tl.x_full[slot], XSLOT_BYTES + TN * (uint32_t)sizeof(float));
           unsigned char* dst = x_base + slot * XSLOT_BYTES;
           tma_load_2d(dst, &maps.x, col0, row0, &tl.x_full[slot]);
           tma_load_2d(dst + X_BOX_BYTES, &maps.x, col0 + SLAB_K, row0, &tl.x_full[slot]);
           bulk_g2s(&tl.b_col[slot][0], bvec + col0, TN * (uint32_t)sizeof(float), &tl.x_full[slot]);   // bvec padded to 64
-        };
-        for (int it = 0; ok && it < ring - 1 && it < ntiles; ++it) issue_x(it);      // X runs ring-1 tiles ahead
-        for (int it = 0; ok && it < ntiles; ++it) {
+        }
+      }
+      __syncwarp();
+    } else if (warp == BPRODUCER_WARP) {
+      // ================= TMA producer of the B operand (one elected thread) =================
+      if (elect_one()) {
+        for (int it = 0; it < ntiles; ++it) {
           const uint32_t u = use + it, bs = u % (uint32_t)nbst, bph = (u / (uint32_t)nbst) & 1;
           const int col0 = (int)((ct_begin + it) * TN);
           if (u >= (uint32_t)nbst && !mbar_wait(&tl.b_free[bs], bph ^ 1, err)) break;   // B stage free again
@@ -472,7 +454,6 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
             tma_load_2d(bh + sl * B_SLAB_BYTES, &maps.v_hi, sl * SLAB_K, col0, &tl.b_full[bs]);
             tma_load_2d(bl + sl * B_SLAB_BYTES, &maps.v_lo, sl * SLAB_K, col0, &tl.b_full[bs]);
           }
-          if (it + ring - 1 < ntiles) issue_x(it + ring - 1);
         }
       }
       __syncwarp();
