@@ -152,3 +152,12 @@ def ptr(t):
 def current_stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def wait_for_stream(dev=None):
+    """Block until the current stream of `dev` is idle.  Stream.synchronize releases the GIL; a thread that waits for
+    the GPU inside Tensor.tolist() / .item() / .cpu() instead kept every other Python thread of a concurrent sweep
+    (structure.parameter_scan(concurrency=k)) from running for the length of its GPU work."""
+    import torch
+    with torch.cuda.device(dev):
+        torch.cuda.current_stream().synchronize()

@@ -227,7 +227,7 @@ struct Maps {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U, int64_t n, int64_t m, int d, int kp,
-                 int nbst, int ring, float s, const float* __restrict__ avec, const float* __restrict__ bvec, int col_splits,
+                 int nbst, int ring, float s, const float* __restrict__ avec, const float* __restrict__ bvec, int probe,
                  double* __restrict__ row_stats, int* __restrict__ error_flag) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with shared-space arithmetic so the compiler keeps LDS/STS addressing
@@ -271,7 +271,6 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
   // Balanced persistent schedule: the row-major tile sequence is cut into gridDim.x equal ranges (+-1 tile);
   // a CTA walks its range one row block at a time (row blocks x fixed column splits left 24 of 148 CTAs with
   // a third work item while the others idled: 72 % wave efficiency).
-  (void)col_splits;
   const int64_t total_tiles = row_tiles * col_tiles;
   const int64_t t_begin = total_tiles * blockIdx.x / gridDim.x;
   const int64_t t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
@@ -343,8 +342,22 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
         const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
         const int64_t col0 = (ct_begin + it) * TN + half * 32;
         if (!mbar_wait(&tl.x_full[slot], xph, err)) break;      // X tile + column means landed
+        if (probe == 1) {                                       // microbenchmark: the X stream alone
+          mbar_arrive(&tl.x_free[slot]);
+          slot += 2;
+          if (slot >= (uint32_t)ring) { slot -= (uint32_t)ring; xph ^= 1; }
+          continue;
+        }
         if (!mbar_wait(&tl.mma_done[st], ph, err)) break;       // accumulators complete
         tc_fence_after();
+        if (probe == 2) {                                       // microbenchmark: X stream + MMAs, no epilogue math
+          tc_fence_before();
+          mbar_arrive(&tl.tmem_free[st]);
+          mbar_arrive(&tl.x_free[slot]);
+          slot += 2;
+          if (slot >= (uint32_t)ring) { slot -= (uint32_t)ring; xph ^= 1; }
+          continue;
+        }
         uint32_t w[32];
         {
           uint32_t (&wa)[16] = *reinterpret_cast<uint32_t (*)[16]>(&w[0]);
@@ -426,7 +439,8 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       // ================= TMA producer of the X stream (one elected thread) =================
       // X and the B operand have their own producer warps: with one thread issuing both, the request for the B
       // tile of tile t sat behind the wait for a free X ring slot (the ring is full whenever HBM is the limit), so
-      // B ran only ~2 tiles ahead of its MMAs whatever the number of B stages.
+      // B ran only ~2 tiles ahead of its MMAs whatever the number of B stages.  (An L2 prefetch of the X tiles ahead
+      // of the ring, cp.async.bulk.prefetch.tensor, was measured and lost: 0.167 -> 0.196 / 0.242 ms at 8 / 16 tiles.)
       if (elect_one()) {
         for (int it = 0; it < ntiles; ++it) {
           const uint32_t u = use + it, slot = u % (uint32_t)ring, xph = (u / (uint32_t)ring) & 1;
@@ -442,7 +456,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       __syncwarp();
     } else if (warp == BPRODUCER_WARP) {
       // ================= TMA producer of the B operand (one elected thread) =================
-      if (elect_one()) {
+      if (probe != 1 && elect_one()) {
         for (int it = 0; it < ntiles; ++it) {
           const uint32_t u = use + it, bs = u % (uint32_t)nbst, bph = (u / (uint32_t)nbst) & 1;
           const int col0 = (int)((ct_begin + it) * TN);
@@ -464,7 +478,7 @@ k_recon_stats_tc(const __grid_constant__ Maps maps, const float* __restrict__ U,
       // showed 28 % of all warp samples on the epilogue's mma_done wait while nothing was saturated (DRAM 39 %, tensor
       // pipe 29 %, issue 45 %) and neither more B stages nor a deeper X ring moved the time.  With four the MMAs run
       // up to three tiles ahead of the epilogue.
-      if (elect_one()) {
+      if (probe != 1 && elect_one()) {
         bool ok = mbar_wait(&tl.a_full, item & 1, err);
         for (int it = 0; ok && it < ntiles; ++it) {
           const uint32_t u = use + it, st = u % NSTAGE, ph = (u / NSTAGE) & 1;
@@ -625,8 +639,11 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   if (ring > tc::MAX_RING) ring = tc::MAX_RING;
   while (ring > 2 && tc::smem_bytes(nslab, nbst, ring) > 232448u) --ring;
   const size_t smem = tc::smem_bytes(nslab, nbst, ring);
+  // MFCD_K5_PROBE (tools/bench_k5.py --probe): pipeline microbenchmarks whose RESULTS ARE INVALID -- 1: the X stream
+  // alone (TMA ring + barriers), 2: X stream + MMAs without the epilogue arithmetic.  0 / unset: the real kernel.
+  const int probe = getenv("MFCD_K5_PROBE") ? atoi(getenv("MFCD_K5_PROBE")) : 0;
   MFCD_CUDA(cudaFuncSetAttribute(tc::k_recon_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, U, n, m, d, kp, nbst, ring, s, avec, bvec, (int)splits,
+  tc::k_recon_stats_tc<<<(int)blocks, tc::NTHREADS, smem, st>>>(maps, U, n, m, d, kp, nbst, ring, s, avec, bvec, probe,
                                                                row_stats, error_flag);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;

@@ -16,7 +16,7 @@ import os
 import numpy as np
 import torch
 
-from ._lib import lib, check, ptr, current_stream, MfcdError
+from ._lib import lib, check, ptr, current_stream, wait_for_stream, MfcdError
 from .store import GroundTruth, compute_device
 
 
@@ -40,6 +40,7 @@ def _combine_rows(t, world):
 def _row_stats(model, gt: GroundTruth, s: float, engine=None, world_size=1):
     """(n x 8) fp64 row statistics of mfcd_recon_stats as a numpy array, and the model's flat state."""
     stats, fs = _row_stats_device(model, gt, s, engine=engine, world_size=world_size)
+    wait_for_stream(stats.device)
     return stats.cpu().numpy(), fs
 
 
@@ -77,6 +78,7 @@ def _row_stats_device(model, gt: GroundTruth, s: float, engine=None, world_size=
                 rc = lib.mfcd_recon_stats_tc(ptr(Ul), ptr(fs.V), nl, m, d, C.byref(xv), float(s), ptr(ubar),
                                              ptr(vbar), ptr(sl), ptr(flag), ptr(ws), need.value, st)
                 if rc == 0:
+                    wait_for_stream(dev)
                     if int(flag.item()) == 0:
                         done = True
                     elif engine == "tc":
@@ -174,6 +176,7 @@ def row_spearman(model, gt: GroundTruth, rows_mask=None, max_bytes=2 << 30, worl
             check(lib.mfcd_row_ranks(ptr(wrows), nr, m, ptr(rw), ptr(ws), ws.numel(), st), "mfcd_row_ranks(W)")
             check(lib.mfcd_row_pearson(ptr(rx), ptr(rw), nr, m, ptr(rho[r0:]), st), "mfcd_row_pearson")
         _combine_rows(rho, world)
+    wait_for_stream(rho.device)
     return rho.cpu().numpy()
 
 

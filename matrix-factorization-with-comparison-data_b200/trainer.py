@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, check, ptr, current_stream
+from ._lib import lib, check, ptr, current_stream, wait_for_stream
 from .store import GroundTruth, HostTripletLoader, TripletLoader, TripletStore, as_loader, compute_device
 
 MODE_ATOMIC = 0
@@ -268,6 +268,8 @@ def eval_batches(fs: _FlatState, store: TripletStore, batch_size):
 
 def _sum_like_python(values):
     """`total += loss.item()` over float32 values, in double, in order."""
+    if isinstance(values, torch.Tensor) and values.is_cuda:
+        wait_for_stream(values.device)
     tot = 0.0
     for v in (values if isinstance(values, list) else values.tolist()):
         tot += v
@@ -456,7 +458,8 @@ def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=1
     """Same contract as the reference's train_model (structure.py:812-878):
     returns ``(train_losses, val_losses)``, one mean-of-batch-means per epoch.
 
-    Per epoch the whole batch loop runs without a host sync (the reference syncs on ``loss.item()`` every step).
+    The whole training runs without a host sync (the reference syncs on ``loss.item()`` every step); the per-epoch
+    losses are read once at the end.
     Keyword-only extras (reference behaviour by default): ``mode`` = scatter mode ('auto': deterministic up to
     256 triplets per batch, atomic above); ``world_size`` > 1 (or a torchrun environment) = data-parallel training,
     every rank passing ITS shard of the triplets and ``train_loader.batch_size`` meaning the GLOBAL batch."""
@@ -480,18 +483,25 @@ def train_model(model, train_loader, val_loader, optimizer, device, num_epochs=1
     if progress and rank == 0:
         from tqdm import tqdm
         epochs = tqdm(epochs, desc="Training Progress")
+    pending = []                                       # single process: per-epoch device tensors, read after the loop
     for _ in epochs:
         step_losses = train_epoch(fs, train_loader, spec, scatter, dp=dp)
         val_loader.begin_iteration()
         vloss, _ = eval_batches(fs, val_loader.store, val_loader.batch_size)
-        # one host sync per epoch
         if world > 1:       # step_losses already holds the GLOBAL batch means (all-reduced once per epoch)
             train_losses.append(_sum_like_python(step_losses) / len(step_losses))
             vsum, vcnt = _all_sum([_sum_like_python(vloss), len(val_loader)], dev, world)
+            val_losses.append(vsum / vcnt)
         else:
+            pending.append((step_losses, vloss))
+    if pending:
+        # ONE host sync for the whole training (the reference syncs on loss.item() every step): the epochs run back to
+        # back on the GPU, and the wait happens in Stream.synchronize, which releases the GIL -- a sweep worker that
+        # waited inside Tensor.tolist() kept the caller thread of a concurrent sweep from preparing the next repetition
+        wait_for_stream(dev)
+        for step_losses, vloss in pending:
             train_losses.append(_sum_like_python(step_losses) / len(train_loader))
-            vsum, vcnt = _sum_like_python(vloss), len(val_loader)
-        val_losses.append(vsum / vcnt)                                    # ZeroDivisionError like the reference
+            val_losses.append(_sum_like_python(vloss) / len(val_loader))      # ZeroDivisionError like the reference
     _export_optimizer_state(model, optimizer, fs, spec)
     if device is not None and torch.device(device).type == "cpu":
         model.mirror_to_host()
