@@ -628,7 +628,7 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   if (blocks > sms) blocks = sms;                                // persistent: one CTA per SM
   const int nslab = kpad / tc::SLAB_K;
   // shared-memory split between B stages and X ring slots (both want ~3 tiles in flight), by operand size
-  static const int kBst[5] = {0, 4, 3, 2, 2};
+  static const int kBst[5] = {0, 3, 3, 2, 2};     // with the even ring: 4 / 4 / 4 / 2 slots (measured best, r02 notes)
   int nbst = kBst[nslab];
   if (getenv("MFCD_K5_BSTAGES")) nbst = atoi(getenv("MFCD_K5_BSTAGES"));
   if (nbst < 2) nbst = 2;
@@ -638,6 +638,13 @@ extern "C" int mfcd_recon_stats_tc(const float* U, const float* V, int64_t n, in
   if (getenv("MFCD_K5_RING")) ring = atoi(getenv("MFCD_K5_RING"));
   if (ring > tc::MAX_RING) ring = tc::MAX_RING;
   while (ring > 2 && tc::smem_bytes(nslab, nbst, ring) > 232448u) --ring;
+  // The ring depth must be EVEN: the two epilogue groups take alternate tiles, so with an even ring every slot is
+  // always served by the same group, in order.  With an odd ring the groups share slots, and a parity wait only
+  // looks at the barrier's current phase bit: a group that runs ahead asks for "tile u + ring has landed" while
+  // tile u (the other group's, same slot) is still in flight and passes at once -- stale data, double arrivals on
+  // x_free and soon a trap (seen as intermittent launch failures at ring = 3 and 5).
+  ring &= ~1;
+  if (ring < 2) ring = 2;
   const size_t smem = tc::smem_bytes(nslab, nbst, ring);
   // MFCD_K5_PROBE (tools/bench_k5.py --probe): pipeline microbenchmarks whose RESULTS ARE INVALID -- 1: the X stream
   // alone (TMA ring + barriers), 2: X stream + MMAs without the epilogue arithmetic.  0 / unset: the real kernel.
