@@ -209,11 +209,17 @@ int mfcd_dp_fused_adam(const uint64_t* peer_grads, const uint64_t* peer_params, 
  * reduce-scatter + Adam + all-gather, writes zeros over the gradient slice it consumed in every rank's buffer,
  * then its last CTA publishes done[rank] = seq and waits for all done[] >= seq before exiting.  `seq` must grow by
  * one per call, identically on all ranks, starting at 1.  cta_counter: one zeroed device word reused across
- * calls.  *error (device) becomes 1 if a bounded spin timed out (results are then invalid). */
+ * calls.  *error (device) becomes 1 if a bounded spin timed out (results are then invalid).
+ * zero_local != NULL: DOUBLE-BUFFERED gradients.  The caller alternates two peer-mapped gradient buffers (step k
+ * accumulates into buffer k & 1 and passes that buffer's peer table); zero_local is THIS rank's other buffer
+ * (numel floats padded to a multiple of 4, 16-byte aligned), which the kernel clears with local stores instead of
+ * writing zeros over the consumed slices through the fabric -- every peer finished reading it before the previous
+ * call returned (the done[] exchange).  Both buffers must start zeroed. */
 int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_flags,
                             uint64_t mc_grads, uint64_t mc_params, int32_t rank, int32_t world, int64_t numel,
                             float* m, float* v, float lr, float beta1, float beta2, float eps, float weight_decay,
-                            int64_t step, uint32_t seq, uint32_t* cta_counter, int32_t* error, void* stream);
+                            int64_t step, uint32_t seq, uint32_t* cta_counter, int32_t* error, float* zero_local,
+                            void* stream);
 
 /* ---- one training epoch, launched from C ------------------------------------
  * The inner loop of train_model (structure.py:845-852) for one epoch on one GPU:

@@ -83,7 +83,7 @@ SIGNATURES = {
     "mfcd_dp_fused_adam": [C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32, F32, F32, F32, F32,
                            I64, P],
     "mfcd_dp_fused_adam_sync": [C.POINTER(U64), C.POINTER(U64), C.POINTER(U64), U64, U64, I32, I32, I64, P, P, F32,
-                                F32, F32, F32, F32, I64, C.c_uint32, P, P, P],
+                                F32, F32, F32, F32, I64, C.c_uint32, P, P, P, P],
     "mfcd_train_epoch": [C.POINTER(EpochArgs)],
     "mfcd_train_epoch_workspace": [C.POINTER(EpochArgs), C.POINTER(SZ)],
     "mfcd_triplet_eval": [P, P, P, I64, I32, I64, P, P, P, P],

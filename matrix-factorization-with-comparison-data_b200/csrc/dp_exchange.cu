@@ -112,8 +112,11 @@ k_dp_fused_adam(PeerTable grads, PeerTable params, const float* __restrict__ mc_
 //   start:  CTA 0 publishes ready[rank] = seq into every rank's flag array (K1 of this step has completed in
 //           stream order, its reductions are in this GPU's L2 where peer loads are served);
 //           every CTA waits until all ranks' ready[] >= seq (acquire, system scope);
-//   body:   reduce-scatter of the owned slice -> Adam -> all-gather, and the owner writes ZEROS over the slice it
-//           has just consumed in every rank's gradient buffer (so the next K1 accumulates into a clean buffer);
+//   body:   reduce-scatter of the owned slice -> Adam -> all-gather.  The next K1 needs a clean gradient buffer:
+//           with `zero_local` the gradients are DOUBLE-BUFFERED -- step k accumulates into buffer k & 1, and this
+//           kernel clears the rank's OTHER buffer locally (every peer finished reading it before the previous K9
+//           completed, see `end`), so no zeros cross the fabric; without it the owner writes zeros over the slice
+//           it has just consumed in every rank's buffer (as much NVLink traffic again as the all-gather);
 //   end:    the last CTA to finish publishes done[rank] = seq everywhere and waits for every rank's done[] >= seq
 //           before it exits: the kernel -- and with it the next K1 in the stream -- cannot complete / start
 //           before all replicas are written and all gradient slices are cleared.
@@ -144,22 +147,26 @@ __global__ void __launch_bounds__(256, 4)
 k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* __restrict__ mc_grads,
                      float* __restrict__ mc_params, int rank, int world, int64_t begin, int64_t end,
                      float* __restrict__ m, float* __restrict__ v, AdamK s, uint32_t seq,
-                     unsigned int* __restrict__ cta_counter, int* __restrict__ error) {
+                     unsigned int* __restrict__ cta_counter, int* __restrict__ error, float* __restrict__ zero_local,
+                     int64_t zero_n4) {
   uint32_t* mine = flags.p[rank];
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(flags.p[threadIdx.x] + rank, seq);                     // ready[rank] in rank threadIdx.x's array
   }
-  if (threadIdx.x < world) {
-    if (!spin_until(mine + threadIdx.x, seq)) atomicExch(error, 1);
-  }
-  __syncthreads();
-
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = (end - begin) >> 2;
   float* my_params = params.p[rank];
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the other gradient buffer, whole, local stores only -- needs nothing from the peers, so it is cleared while
+  // the slower ranks are still finishing their K1
+  if (zero_local != nullptr)
+    for (int64_t k = tid; k < zero_n4; k += nth) reinterpret_cast<float4*>(zero_local)[k] = zero4;
+  if (threadIdx.x < world) {
+    if (!spin_until(mine + threadIdx.x, seq)) atomicExch(error, 1);
+  }
+  __syncthreads();
   for (int64_t k = tid; k < n4; k += nth) {
     const int64_t e = begin + (k << 2);
     float4 g;
@@ -188,14 +195,16 @@ k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* 
     // gradient loads have RETURNED: clearing a slice can never overtake the read of that slice.
     if (MULTIMEM) {
       multimem_st(mc_params + e, pp);
-      multimem_st(mc_grads + e, zero4);
+      if (zero_local == nullptr) multimem_st(mc_grads + e, zero4);
     } else {
 #pragma unroll
       for (int q = 0; q < kMaxPeers; ++q)
         if (q < world) *reinterpret_cast<float4*>(params.p[q] + e) = pp;
+      if (zero_local == nullptr) {
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; ++q)
-        if (q < world) *reinterpret_cast<float4*>(grads.p[q] + e) = zero4;
+        for (int q = 0; q < kMaxPeers; ++q)
+          if (q < world) *reinterpret_cast<float4*>(grads.p[q] + e) = zero4;
+      }
     }
   }
   for (int64_t e = begin + (n4 << 2) + tid; e < end; e += nth) {        // ragged tail of the last owner
@@ -205,7 +214,8 @@ k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* 
     adam_one(pp, g, mm, vv, s);
     m[e] = mm; v[e] = vv;
     for (int q = 0; q < world; ++q) params.p[q][e] = pp;
-    for (int q = 0; q < world; ++q) grads.p[q][e] = 0.f;
+    if (zero_local == nullptr)
+      for (int q = 0; q < world; ++q) grads.p[q][e] = 0.f;
   }
 
   // all of this CTA's peer stores are ordered before its arrival at the counter
@@ -232,7 +242,8 @@ extern "C" int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_
                                        const uint64_t* peer_flags, uint64_t mc_grads, uint64_t mc_params,
                                        int32_t rank, int32_t world, int64_t numel, float* m, float* v, float lr,
                                        float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                                       uint32_t seq, uint32_t* cta_counter, int32_t* error, void* stream) {
+                                       uint32_t seq, uint32_t* cta_counter, int32_t* error, float* zero_local,
+                                       void* stream) {
   MFCD_REQUIRE(peer_grads && peer_params && peer_flags && m && v && cta_counter && error,
                "mfcd_dp_fused_adam_sync: NULL pointer");
   MFCD_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "mfcd_dp_fused_adam_sync: world must be 1..8");
@@ -264,16 +275,19 @@ extern "C" int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_
   // every CTA spins at the start, so the whole grid must be co-resident: at most 4 CTAs of 256 threads per SM
   // (the launch bound keeps the kernel at <= 64 registers).  A rank with an empty slice still takes part in the
   // flag exchange (one CTA).
-  int grid = grid_for((end - begin + 3) / 4, 256, 4);
-  if (end <= begin) grid = 1;
+  // zero_local: a buffer of numel floats padded to a multiple of 4 (the exchange allocates it that way)
+  const int64_t zero_n4 = zero_local ? (numel + 3) / 4 : 0;
+  MFCD_REQUIRE((reinterpret_cast<uintptr_t>(zero_local) & 15u) == 0, "mfcd_dp_fused_adam_sync: zero_local must be 16-byte aligned");
+  int grid = grid_for((end - begin + 3) / 4 + zero_n4, 256, 4);
+  if (end <= begin && zero_n4 == 0) grid = 1;
   cudaStream_t st = as_stream(stream);
   if (mc_grads != 0 && mc_params != 0)
     k_dp_fused_adam_sync<true><<<grid, 256, 0, st>>>(g, p, f, reinterpret_cast<float*>(mc_grads),
                                                      reinterpret_cast<float*>(mc_params), rank, world, begin, end, m, v,
-                                                     s, seq, cta_counter, error);
+                                                     s, seq, cta_counter, error, zero_local, zero_n4);
   else
     k_dp_fused_adam_sync<false><<<grid, 256, 0, st>>>(g, p, f, nullptr, nullptr, rank, world, begin, end, m, v, s, seq,
-                                                      cta_counter, error);
+                                                      cta_counter, error, zero_local, zero_n4);
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }

@@ -150,19 +150,26 @@ class PeerExchange:
         self.numel = numel
         self.params = symm_mem.empty(padded, dtype=torch.float32, device=device)
         self.grads = symm_mem.empty(padded, dtype=torch.float32, device=device)
+        # second gradient buffer (in-kernel sync): step k accumulates into buffer k & 1 while K9 clears the other one
+        # LOCALLY -- no zeros through the fabric (they were as much NVLink traffic again as the all-gather)
+        self.grads_b = symm_mem.empty(padded, dtype=torch.float32, device=device)
         self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)      # ready[8] | done[8] (+ padding)
         self.params.zero_()
         self.grads.zero_()
+        self.grads_b.zero_()
         self.flags.zero_()
         self.hp = symm_mem.rendezvous(self.params, group)
         self.hg = symm_mem.rendezvous(self.grads, group)
+        self.hg_b = symm_mem.rendezvous(self.grads_b, group)
         self.hf = symm_mem.rendezvous(self.flags, group)
         self.rank, self.world = self.hp.rank, self.hp.world_size
         self.peer_params = (C.c_uint64 * self.world)(*[int(x) for x in self.hp.buffer_ptrs])
         self.peer_grads = (C.c_uint64 * self.world)(*[int(x) for x in self.hg.buffer_ptrs])
+        self.peer_grads_b = (C.c_uint64 * self.world)(*[int(x) for x in self.hg_b.buffer_ptrs])
         self.peer_flags = (C.c_uint64 * self.world)(*[int(x) for x in self.hf.buffer_ptrs])
         mc_p = int(getattr(self.hp, "multicast_ptr", 0) or 0)
         mc_g = int(getattr(self.hg, "multicast_ptr", 0) or 0)
+        mc_gb = int(getattr(self.hg_b, "multicast_ptr", 0) or 0)
         # measured on NVSwitch B200 boxes (profiles/r01_notes.md): in-switch multimem reduction wins at 8 ranks
         # (0.134 vs 0.163 ms per exchange), plain peer loads win at 2 (0.094 vs 0.139 ms); equal at 4.
         env = os.environ.get("MFCD_DP_MULTIMEM", "auto")
@@ -170,8 +177,9 @@ class PeerExchange:
             use_multimem = env == "on"
         if use_multimem == "auto":
             use_multimem = self.world > 4
-        self.multimem = bool(use_multimem and mc_p and mc_g)
-        self.mc_params, self.mc_grads = (mc_p, mc_g) if self.multimem else (0, 0)
+        self.multimem = bool(use_multimem and mc_p and mc_g and mc_gb)
+        self.mc_params, self.mc_grads, self.mc_grads_b = (mc_p, mc_g, mc_gb) if self.multimem else (0, 0, 0)
+        self.double_buffer = os.environ.get("MFCD_DP_DOUBLE_BUFFER", "1") != "0"
         # "kernel": flags exchanged inside K9, the owner clears the gradient slices it consumed (default);
         # "barrier": two symmetric-memory barriers around K9 + a local memset (round-1 path, kept for comparison)
         self.sync = sync or os.environ.get("MFCD_DP_SYNC", "kernel")
@@ -199,15 +207,22 @@ class PeerExchange:
         """K9: reduce-scatter + Adam + all-gather in one kernel; leaves the gradient buffers cleared."""
         if spec.kind != 0:
             raise NotImplementedError("the fused peer exchange implements Adam")
-        assert fs.params.data_ptr() == self.params.data_ptr() and fs.grads.data_ptr() == self.grads.data_ptr()
+        assert fs.params.data_ptr() == self.params.data_ptr()
         if self.sync == "kernel":
             self.seq += 1
-            check(lib.mfcd_dp_fused_adam_sync(self.peer_grads, self.peer_params, self.peer_flags, self.mc_grads,
+            in_a = fs.grads.data_ptr() == self.grads.data_ptr()
+            assert in_a or fs.grads.data_ptr() == self.grads_b.data_ptr()
+            peers, mc = (self.peer_grads, self.mc_grads) if in_a else (self.peer_grads_b, self.mc_grads_b)
+            other = (self.grads_b if in_a else self.grads) if self.double_buffer else None
+            check(lib.mfcd_dp_fused_adam_sync(peers, self.peer_params, self.peer_flags, mc,
                                               self.mc_params, self.rank, self.world, self.numel, ptr(fs.state1),
                                               ptr(fs.state2), spec.lr, spec.beta1, spec.beta2, spec.eps,
                                               spec.weight_decay, step, self.seq, ptr(self.cta_counter),
-                                              ptr(self.error), current_stream()), "mfcd_dp_fused_adam_sync")
+                                              ptr(self.error), ptr(other), current_stream()), "mfcd_dp_fused_adam_sync")
+            if other is not None:           # the next K1 accumulates into the buffer this call has just cleared
+                fs.grads = other[:fs.grads.numel()]
             return
+        assert fs.grads.data_ptr() == self.grads.data_ptr()
         self.hg.barrier(channel=0)
         check(lib.mfcd_dp_fused_adam(self.peer_grads, self.peer_params, self.mc_grads, self.mc_params, self.rank,
                                      self.world, self.numel, ptr(fs.state1), ptr(fs.state2), spec.lr, spec.beta1,

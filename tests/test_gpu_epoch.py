@@ -211,7 +211,7 @@ def test_fused_exchange_with_in_kernel_flags_on_one_rank(G, numel):
         gnp = rng.standard_normal(numel).astype(np.float32)
         g.copy_(torch.from_numpy(gnp)); gr.copy_(torch.from_numpy(gnp))
         check(lib.mfcd_dp_fused_adam_sync(arr(g), arr(p), arr(flags), 0, 0, 0, 1, numel, ptr(m1), ptr(v1), 1e-2, 0.9,
-                                          0.999, 1e-8, 1e-4, step, step, ptr(counter), ptr(err), current_stream()), "k9")
+                                          0.999, 1e-8, 1e-4, step, step, ptr(counter), ptr(err), None, current_stream()), "k9")
         check(lib.mfcd_adam_update(ptr(pr), ptr(gr), ptr(mr), ptr(vr), numel, 1e-2, 0.9, 0.999, 1e-8, 1e-4, step, 1,
                                    current_stream()), "k3")
         torch.cuda.synchronize()
@@ -219,3 +219,22 @@ def test_fused_exchange_with_in_kernel_flags_on_one_rank(G, numel):
         assert torch.equal(p, pr) and torch.equal(m1, mr) and torch.equal(v1, vr)
         assert not g.any()
     assert flags[0].item() == 3 and flags[8].item() == 3
+    # double-buffered gradients: the call consumes one buffer (left as is) and clears the OTHER one locally
+    padded = (numel + 3) // 4 * 4
+    bufs = [torch.zeros(padded, device=G.DEV), torch.zeros(padded, device=G.DEV)]
+    for step in range(4, 8):
+        cur, other = bufs[step & 1], bufs[(step + 1) & 1]
+        gnp = rng.standard_normal(numel).astype(np.float32)
+        assert not cur.any()                                   # cleared by the previous call (or never used)
+        cur[:numel].copy_(torch.from_numpy(gnp)); gr.copy_(torch.from_numpy(gnp))
+        other.fill_(7.0)                                       # whatever the step before the previous one left
+        check(lib.mfcd_dp_fused_adam_sync(arr(cur), arr(p), arr(flags), 0, 0, 0, 1, numel, ptr(m1), ptr(v1), 1e-2, 0.9,
+                                          0.999, 1e-8, 1e-4, step, step, ptr(counter), ptr(err), ptr(other),
+                                          current_stream()), "k9")
+        check(lib.mfcd_adam_update(ptr(pr), ptr(gr), ptr(mr), ptr(vr), numel, 1e-2, 0.9, 0.999, 1e-8, 1e-4, step, 1,
+                                   current_stream()), "k3")
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        assert torch.equal(p, pr) and torch.equal(m1, mr) and torch.equal(v1, vr)
+        assert not other.any() and torch.equal(cur[:numel].cpu(), torch.from_numpy(gnp))
+        cur.zero_()
