@@ -496,7 +496,7 @@ def main():
             "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_lean (K1 fused fwd+bwd)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_span (K1 fused fwd+bwd, user-grouped batches)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_triplet": bytes_per_triplet, "k1_ms": k1_ms,
                          "dram_frac": (traffic / (k1_ms * 1e-3) / 1e9 / peak) if traffic else None,

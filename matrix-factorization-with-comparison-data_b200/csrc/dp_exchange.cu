@@ -142,8 +142,12 @@ __device__ __forceinline__ bool spin_until(const uint32_t* word, uint32_t seq) {
   return true;
 }
 
-template <bool MULTIMEM>
-__global__ void __launch_bounds__(256, 4)
+// W = number of peer loads per element on the p2p path (compile-time, so the in-flight registers are exactly W x UNR
+// float4), UNR = elements whose gradient loads are ALL issued before the first one is consumed.  A remote load
+// takes ~4-5 us through the switch; with one element in flight per thread the 8 dependent iterations of a 2-rank
+// slice alone cost ~40 us of the 85 us the kernel took (tools/k9_diag.py), so the loads of UNR elements overlap.
+template <bool MULTIMEM, int W, int UNR>
+__global__ void __launch_bounds__(256, 3)
 k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* __restrict__ mc_grads,
                      float* __restrict__ mc_params, int rank, int world, int64_t begin, int64_t end,
                      float* __restrict__ m, float* __restrict__ v, AdamK s, uint32_t seq,
@@ -167,43 +171,58 @@ k_dp_fused_adam_sync(PeerTable grads, PeerTable params, FlagTable flags, float* 
     if (!spin_until(mine + threadIdx.x, seq)) atomicExch(error, 1);
   }
   __syncthreads();
-  for (int64_t k = tid; k < n4; k += nth) {
-    const int64_t e = begin + (k << 2);
-    float4 g;
-    if (MULTIMEM) {
-      g = multimem_ld_reduce_add(mc_grads + e);
-    } else {
-      g = zero4;
+
+  for (int64_t k0 = tid; k0 < n4; k0 += nth * UNR) {
+    float4 g[UNR], t[UNR][MULTIMEM ? 1 : W];
+    // 1. every gradient load of the UNR elements goes out before anything waits for one
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; ++q) {
-        if (q < world) {
-          const float4 t = __ldcv(reinterpret_cast<const float4*>(grads.p[q] + e));
-          g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t k = k0 + u * nth;
+      if (k < n4) {
+        const int64_t e = begin + (k << 2);
+        if (MULTIMEM) {
+          t[u][0] = multimem_ld_reduce_add(mc_grads + e);
+        } else {
+#pragma unroll
+          for (int q = 0; q < W; ++q)
+            t[u][q] = __ldcv(reinterpret_cast<const float4*>(grads.p[q] + e));      // peer data: never a stale L1 line
         }
       }
     }
-    float4 pp = *reinterpret_cast<const float4*>(my_params + e);
-    float4 mm = *reinterpret_cast<const float4*>(m + e);
-    float4 vv = *reinterpret_cast<const float4*>(v + e);
-    adam_one(pp.x, g.x, mm.x, vv.x, s);
-    adam_one(pp.y, g.y, mm.y, vv.y, s);
-    adam_one(pp.z, g.z, mm.z, vv.z, s);
-    adam_one(pp.w, g.w, mm.w, vv.w, s);
-    *reinterpret_cast<float4*>(m + e) = mm;
-    *reinterpret_cast<float4*>(v + e) = vv;
-    // The parameter stores depend on g, so a warp (in-order issue) reaches the zero stores below only after the
-    // gradient loads have RETURNED: clearing a slice can never overtake the read of that slice.
-    if (MULTIMEM) {
-      multimem_st(mc_params + e, pp);
-      if (zero_local == nullptr) multimem_st(mc_grads + e, zero4);
-    } else {
+    // 2. sums in rank order (deterministic), Adam on the owned slice, all-gather
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; ++q)
-        if (q < world) *reinterpret_cast<float4*>(params.p[q] + e) = pp;
-      if (zero_local == nullptr) {
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t k = k0 + u * nth;
+      if (k >= n4) continue;
+      const int64_t e = begin + (k << 2);
+      if (MULTIMEM) {
+        g[u] = t[u][0];
+      } else {
+        g[u] = zero4;
 #pragma unroll
-        for (int q = 0; q < kMaxPeers; ++q)
-          if (q < world) *reinterpret_cast<float4*>(grads.p[q] + e) = zero4;
+        for (int q = 0; q < W; ++q) { g[u].x += t[u][q].x; g[u].y += t[u][q].y; g[u].z += t[u][q].z; g[u].w += t[u][q].w; }
+      }
+      float4 pp = *reinterpret_cast<const float4*>(my_params + e);
+      float4 mm = *reinterpret_cast<const float4*>(m + e);
+      float4 vv = *reinterpret_cast<const float4*>(v + e);
+      adam_one(pp.x, g[u].x, mm.x, vv.x, s);
+      adam_one(pp.y, g[u].y, mm.y, vv.y, s);
+      adam_one(pp.z, g[u].z, mm.z, vv.z, s);
+      adam_one(pp.w, g[u].w, mm.w, vv.w, s);
+      *reinterpret_cast<float4*>(m + e) = mm;
+      *reinterpret_cast<float4*>(v + e) = vv;
+      // The parameter stores depend on g, so a warp (in-order issue) reaches the zero stores below only after the
+      // gradient loads have RETURNED: clearing a slice can never overtake the read of that slice.
+      if (MULTIMEM) {
+        multimem_st(mc_params + e, pp);
+        if (zero_local == nullptr) multimem_st(mc_grads + e, zero4);
+      } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(params.p[q] + e) = pp;
+        if (zero_local == nullptr) {
+#pragma unroll
+          for (int q = 0; q < W; ++q) *reinterpret_cast<float4*>(grads.p[q] + e) = zero4;
+        }
       }
     }
   }
@@ -272,22 +291,29 @@ extern "C" int mfcd_dp_fused_adam_sync(const uint64_t* peer_grads, const uint64_
   s.one_minus_b2 = (float)(1.0 - (double)beta2);
   s.eps = eps;
   s.wd = weight_decay;
-  // every CTA spins at the start, so the whole grid must be co-resident: at most 4 CTAs of 256 threads per SM
-  // (the launch bound keeps the kernel at <= 64 registers).  A rank with an empty slice still takes part in the
+  // every CTA spins at the start, so the whole grid must be co-resident: at most 3 CTAs of 256 threads per SM
+  // (the launch bound keeps the kernel at <= 85 registers).  A rank with an empty slice still takes part in the
   // flag exchange (one CTA).
   // zero_local: a buffer of numel floats padded to a multiple of 4 (the exchange allocates it that way)
   const int64_t zero_n4 = zero_local ? (numel + 3) / 4 : 0;
   MFCD_REQUIRE((reinterpret_cast<uintptr_t>(zero_local) & 15u) == 0, "mfcd_dp_fused_adam_sync: zero_local must be 16-byte aligned");
-  int grid = grid_for((end - begin + 3) / 4 + zero_n4, 256, 4);
+  int grid = grid_for((end - begin + 3) / 4 + zero_n4, 256, 3);
   if (end <= begin && zero_n4 == 0) grid = 1;
   cudaStream_t st = as_stream(stream);
-  if (mc_grads != 0 && mc_params != 0)
-    k_dp_fused_adam_sync<true><<<grid, 256, 0, st>>>(g, p, f, reinterpret_cast<float*>(mc_grads),
-                                                     reinterpret_cast<float*>(mc_params), rank, world, begin, end, m, v,
-                                                     s, seq, cta_counter, error, zero_local, zero_n4);
-  else
-    k_dp_fused_adam_sync<false><<<grid, 256, 0, st>>>(g, p, f, nullptr, nullptr, rank, world, begin, end, m, v, s, seq,
-                                                      cta_counter, error, zero_local, zero_n4);
+#define MFCD_K9_GO(MM, W, UNR)                                                                                   \
+  k_dp_fused_adam_sync<MM, W, UNR><<<grid, 256, 0, st>>>(g, p, f, reinterpret_cast<float*>(mc_grads),                \
+                                                         reinterpret_cast<float*>(mc_params), rank, world, begin, end, \
+                                                         m, v, s, seq, cta_counter, error, zero_local, zero_n4)
+  if (mc_grads != 0 && mc_params != 0) MFCD_K9_GO(true, 1, 4);
+  else if (world == 1) MFCD_K9_GO(false, 1, 4);
+  else if (world == 2) MFCD_K9_GO(false, 2, 4);
+  else if (world == 3) MFCD_K9_GO(false, 3, 2);
+  else if (world == 4) MFCD_K9_GO(false, 4, 2);
+  else if (world == 5) MFCD_K9_GO(false, 5, 1);
+  else if (world == 6) MFCD_K9_GO(false, 6, 1);
+  else if (world == 7) MFCD_K9_GO(false, 7, 1);
+  else MFCD_K9_GO(false, 8, 1);
+#undef MFCD_K9_GO
   MFCD_CHECK_LAUNCH();
   return MFCD_OK;
 }

@@ -76,7 +76,7 @@ if rank == 0:
     n_train = int(counts[0])
     res = {"config": vars(a), "world": world, "gpu": torch.cuda.get_device_name(0),
            "triplets": {"requested": total, "train": n_train, "val": int(counts[1]), "test": int(counts[2])},
-           "global_batch": B, "steps_per_epoch": len(train_loader), "phases_s": times,
+           "global_batch": B, "steps_per_epoch": -(-n_train // B), "phases_s": times,
            "train_triplets_per_s": n_train * a.epochs / times[[k for k in times if k.startswith("train_model")][0]],
            "train_losses": tl, "val_losses": vl, "test_loss": test_loss, "test_accuracy": test_acc,
            "ground_truth_mse": gt_loss, "ground_truth_accuracy": gt_acc,
