@@ -161,16 +161,37 @@ int mfcd_group_by_user_workspace(int64_t N, int64_t batch_size, size_t* bytes);
 int mfcd_group_by_user(mfcd_triplet* rec, int64_t N, int64_t batch_size, void* workspace, size_t workspace_bytes,
                        void* stream);
 
-/* ---- K1+K2: deterministic variant ------------------------------------------
- * Same contract, but run-to-run bit-reproducible: per-row gradient sums are
- * formed by sorting the batch by destination row (stable, so batch order is
- * kept inside a row, the order the reference's CPU index_put_ uses) and a
- * segmented reduction; the loss is reduced in a fixed order. */
+/* ---- K1 deterministic variant ------------------------------------------------
+ * Same contract, but run-to-run bit-reproducible.
+ *   B <= 256 (the reference's regime): one CTA sums every row's contributions in batch order, the order of the
+ *   reference's sequential CPU index_put_(accumulate);
+ *   larger B, engine "fixed" (k1_fixed.cu; default up to 16384 triplets per batch): every contribution g * x is
+ *   rounded once to 64-bit fixed point and added with integer atomics into a 64-bit image of the gradient tables
+ *   held in the workspace (integer sums do not depend on the order the atomics land in -- nor on the order of the
+ *   batch), then converted to fp32 with one rounding per element and added to gU / gV; the loss likewise.  Two
+ *   launches, no sort;
+ *   larger B, engine "sort" (segmented.cu; default above 16384): stable radix sort by destination row
+ *   (cub::DeviceRadixSort) + segmented reduction, batch order kept inside a row; 17 launches, but vector fp32
+ *   traffic: faster on big batches (64-bit atomics run at a quarter of the vector-fp32 reduction rate and
+ *   serialise on hot rows).
+ * mfcd_det_workspace_bytes_nm = what the default engine for this B wants; MFCD_DET_ENGINE=fixed|sort (environment)
+ * forces one engine; the _fixed / _sort entry points select one explicitly. */
 int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes);
+int mfcd_det_workspace_bytes_nm(int64_t B, int32_t d, int64_t n_users, int64_t n_items, size_t* bytes);
 int mfcd_triplet_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                              int64_t start, int64_t B, int32_t d, float inv_batch, int64_t n_users,
                              int64_t n_items, float* gU, float* gV, float* loss, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* the two engines under their own names (workspaces: mfcd_det_fixed_workspace_bytes / mfcd_det_workspace_bytes) */
+int mfcd_det_fixed_workspace_bytes(int32_t d, int64_t n_users, int64_t n_items, size_t* bytes);
+int mfcd_triplet_fwd_bwd_det_fixed(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                                   int64_t start, int64_t B, int32_t d, float inv_batch, int64_t n_users,
+                                   int64_t n_items, float* gU, float* gV, float* loss, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+int mfcd_triplet_fwd_bwd_det_sort(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
+                                  int64_t start, int64_t B, int32_t d, float inv_batch, int64_t n_users,
+                                  int64_t n_items, float* gU, float* gV, float* loss, void* workspace,
+                                  size_t workspace_bytes, void* stream);
 
 /* ---- K3: fused dense optimiser update --------------------------------------
  * torch.optim.Adam single-tensor semantics with coupled L2 (structure.py:364,

@@ -76,7 +76,11 @@ SIGNATURES = {
     "mfcd_group_by_user_workspace": [I64, I64, C.POINTER(SZ)],
     "mfcd_group_by_user": [P, I64, I64, P, SZ, P],
     "mfcd_det_workspace_bytes": [I64, I32, C.POINTER(SZ)],
+    "mfcd_det_workspace_bytes_nm": [I64, I32, I64, I64, C.POINTER(SZ)],
     "mfcd_triplet_fwd_bwd_det": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
+    "mfcd_triplet_fwd_bwd_det_sort": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
+    "mfcd_triplet_fwd_bwd_det_fixed": [P, P, P, P, I64, I64, I32, F32, I64, I64, P, P, P, P, SZ, P],
+    "mfcd_det_fixed_workspace_bytes": [I32, I64, I64, C.POINTER(SZ)],
     "mfcd_adam_update": [P, P, P, P, I64, F32, F32, F32, F32, F32, I64, I32, P],
     "mfcd_sgd_update": [P, P, P, I64, F32, F32, F32, I64, I32, P],
     "mfcd_dp_shard_range": [I64, I32, I32, C.POINTER(I64), C.POINTER(I64)],

@@ -533,7 +533,8 @@ extern "C" int mfcd_train_epoch_workspace(const mfcd_epoch_args* a, size_t* byte
   size_t need = epoch_small_workspace_bytes(a);
   if (a->mode == MFCD_MODE_DETERMINISTIC && a->batch_size > 0 && a->d >= 1) {
     const int64_t b = a->n_samples < a->batch_size ? a->n_samples : a->batch_size;
-    const size_t det = det_workspace_bytes(b, a->d);
+    const size_t det = (a->n_users >= 1 && a->n_items >= 1) ? det_workspace_bytes_nm(b, a->d, a->n_users, a->n_items)
+                                                            : det_workspace_bytes(b, a->d);
     if (det > need) need = det;
   }
   *bytes = need;

@@ -25,7 +25,13 @@ int max_hot_rows(int d);
 int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm,
                        int64_t start, int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items,
                        float* gU, float* gV, float* loss, void* ws, size_t ws_bytes, cudaStream_t st);
-size_t det_workspace_bytes(int64_t B, int d);
+size_t det_workspace_bytes(int64_t B, int d);                      // sort + segmented reduction engine (segmented.cu)
+// fixed-point engine (k1_fixed.cu): integer atomics into a 64-bit image of the gradient tables, no sort
+size_t det_fixed_workspace_bytes(int64_t n_users, int64_t n_items, int d);
+size_t det_workspace_bytes_nm(int64_t B, int d, int64_t n_users, int64_t n_items);   // what the default engine wants
+int launch_det_fixed(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
+                     int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
+                     float* loss, void* ws, cudaStream_t st);
 
 __device__ __forceinline__ float xview_at(const mfcd_xview& X, int64_t r, int64_t c) {
   if (X.X != nullptr) return __ldg(X.X + r * X.ldx + c);

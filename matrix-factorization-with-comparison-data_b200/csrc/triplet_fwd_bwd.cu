@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "internal.h"
 #include "shape_dispatch.cuh"
+#include <string.h>
 #include "k1_lean.cuh"
 
 namespace mfcd {
@@ -590,15 +591,49 @@ size_t det_workspace_bytes(int64_t B, int d) {
   return det_large_workspace_bytes(B, d);
 }
 
+// Engine of the large-batch deterministic mode.
+//   "fixed" (k1_fixed.cu): integer atomics into a 64-bit fixed-point image of the gradient tables; 2 launches, no
+//           library call, and the result does not even depend on the order of the batch.  64-bit atomics have a
+//           quarter of the vector-fp32 reduction rate and serialise on hot rows, so it wins where the step is
+//           launch-bound and loses on big batches (measured at 2^20 triplets, config-4 tables: 0.98 ms against
+//           0.62 ms uniform, 19 ms against 1.7 ms under zipf(1.5) items; profiles/r02_notes.md);
+//   "sort"  (segmented.cu): three stable radix sorts by destination row (cub::DeviceRadixSort) + a chunked segmented
+//           reduction that keeps batch order inside a row, like the reference's sequential index_put_; 17 launches.
+// Default: fixed up to kFixedMaxB triplets per batch, sort above (tools/det_sweep.py, profiles/r02_det_engines_us.json:
+// uniform items cross over near 5e5 triplets, zipf(1.5) items near 1e4); MFCD_DET_ENGINE=fixed|sort forces one.
+constexpr int64_t kFixedMaxB = 16384;
+static int det_engine_env() {          // 0 = auto, 1 = fixed, 2 = sort
+  static const int v = !getenv("MFCD_DET_ENGINE") ? 0 : (strcmp(getenv("MFCD_DET_ENGINE"), "fixed") == 0 ? 1 :
+                                                         (strcmp(getenv("MFCD_DET_ENGINE"), "sort") == 0 ? 2 : 0));
+  return v;
+}
+static bool det_use_fixed(int64_t B) {
+  const int e = det_engine_env();
+  return e == 1 || (e == 0 && B <= kFixedMaxB);
+}
+
+size_t det_workspace_bytes_nm(int64_t B, int d, int64_t n_users, int64_t n_items) {
+  if (B <= kSmallB) return 0;
+  return det_use_fixed(B) ? det_fixed_workspace_bytes(n_users, n_items, d) : det_large_workspace_bytes(B, d);
+}
+
 int launch_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec, const int32_t* perm, int64_t start,
                        int64_t B, int d, float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
                        float* loss, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (B == 0) return MFCD_OK;
   K1Timer timer(st);
   if (B <= kSmallB) return launch_det_small(U, V, rec, perm, start, (int)B, d, inv_batch, gU, gV, loss, st);
-  const size_t need = det_large_workspace_bytes(B, d);
-  if (ws == nullptr || ws_bytes < need) {
-    set_error("deterministic mode: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+  const size_t need_fix = det_fixed_workspace_bytes(n_users, n_items, d);
+  const size_t need_sort = det_large_workspace_bytes(B, d);
+  const bool fits_fix = ws != nullptr && ws_bytes >= need_fix, fits_sort = ws != nullptr && ws_bytes >= need_sort;
+  // the preferred engine when its workspace is there, else the other one (a caller that sized the workspace with
+  // mfcd_det_workspace_bytes gets the sort engine as before)
+  const bool fixed = det_use_fixed(B) ? (fits_fix || !fits_sort) : !fits_sort && fits_fix;
+  if (fixed && fits_fix)
+    return launch_det_fixed(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, ws, st);
+  if (!fits_sort) {
+    set_error("deterministic mode: workspace too small (%zu bytes; the fixed-point engine wants %zu, the sort "
+              "engine %zu; see mfcd_det_workspace_bytes_nm)", ws_bytes, need_fix, need_sort);
     return MFCD_ERR_WORKSPACE;
   }
   return launch_det_large(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, ws, ws_bytes, st);
@@ -660,6 +695,13 @@ extern "C" int mfcd_det_workspace_bytes(int64_t B, int32_t d, size_t* bytes) {
   return MFCD_OK;
 }
 
+extern "C" int mfcd_det_workspace_bytes_nm(int64_t B, int32_t d, int64_t n_users, int64_t n_items, size_t* bytes) {
+  MFCD_REQUIRE(bytes != nullptr && B >= 0 && d >= 1 && n_users >= 1 && n_items >= 1,
+               "mfcd_det_workspace_bytes_nm: bad argument");
+  *bytes = det_workspace_bytes_nm(B, d, n_users, n_items);
+  return MFCD_OK;
+}
+
 extern "C" int mfcd_triplet_fwd_bwd_det(const float* U, const float* V, const mfcd_triplet* rec,
                                         const int32_t* perm, int64_t start, int64_t B, int32_t d, float inv_batch,
                                         int64_t n_users, int64_t n_items, float* gU, float* gV, float* loss,
@@ -669,6 +711,48 @@ extern "C" int mfcd_triplet_fwd_bwd_det(const float* U, const float* V, const mf
   MFCD_REQUIRE(n_users > 0 && n_items > 0, "mfcd_triplet_fwd_bwd_det: table sizes must be positive");
   return launch_fwd_bwd_det(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, workspace,
                             workspace_bytes, as_stream(stream));
+}
+
+extern "C" int mfcd_triplet_fwd_bwd_det_fixed(const float* U, const float* V, const mfcd_triplet* rec,
+                                              const int32_t* perm, int64_t start, int64_t B, int32_t d,
+                                              float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
+                                              float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd_det_fixed", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(n_users > 0 && n_items > 0, "mfcd_triplet_fwd_bwd_det_fixed: table sizes must be positive");
+  if (B == 0) return MFCD_OK;
+  const size_t need = det_fixed_workspace_bytes(n_users, n_items, d);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("mfcd_triplet_fwd_bwd_det_fixed: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return MFCD_ERR_WORKSPACE;
+  }
+  return launch_det_fixed(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, workspace,
+                          as_stream(stream));
+}
+
+extern "C" int mfcd_det_fixed_workspace_bytes(int32_t d, int64_t n_users, int64_t n_items, size_t* bytes) {
+  MFCD_REQUIRE(bytes != nullptr && d >= 1 && n_users >= 1 && n_items >= 1, "mfcd_det_fixed_workspace_bytes: bad argument");
+  *bytes = det_fixed_workspace_bytes(n_users, n_items, d);
+  return MFCD_OK;
+}
+
+extern "C" int mfcd_triplet_fwd_bwd_det_sort(const float* U, const float* V, const mfcd_triplet* rec,
+                                             const int32_t* perm, int64_t start, int64_t B, int32_t d,
+                                             float inv_batch, int64_t n_users, int64_t n_items, float* gU, float* gV,
+                                             float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common("mfcd_triplet_fwd_bwd_det_sort", U, V, rec, start, B, d, gU, gV, loss);
+  if (rc != MFCD_OK) return rc;
+  MFCD_REQUIRE(n_users > 0 && n_items > 0, "mfcd_triplet_fwd_bwd_det_sort: table sizes must be positive");
+  if (B == 0) return MFCD_OK;
+  if (B <= kSmallB)
+    return launch_det_small(U, V, rec, perm, start, (int)B, d, inv_batch, gU, gV, loss, as_stream(stream));
+  if (workspace == nullptr || workspace_bytes < det_large_workspace_bytes(B, d)) {
+    set_error("mfcd_triplet_fwd_bwd_det_sort: workspace too small (%zu < %zu bytes)", workspace_bytes,
+              det_large_workspace_bytes(B, d));
+    return MFCD_ERR_WORKSPACE;
+  }
+  return launch_det_large(U, V, rec, perm, start, B, d, inv_batch, n_users, n_items, gU, gV, loss, workspace,
+                          workspace_bytes, as_stream(stream));
 }
 
 // one epoch of structure.py:845-852 launched from C (no per-step python)

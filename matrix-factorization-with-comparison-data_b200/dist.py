@@ -103,7 +103,7 @@ class CudaEngine:
         inv = 1.0 / float(b_global)
         if self.mode == 1:
             need = C.c_size_t(0)
-            check(lib.mfcd_det_workspace_bytes(b_local, fs.d, C.byref(need)), "mfcd_det_workspace_bytes")
+            check(lib.mfcd_det_workspace_bytes_nm(b_local, fs.d, fs.n, fs.m, C.byref(need)), "mfcd_det_workspace_bytes_nm")
             ws = fs.ensure_workspace(need.value)
             check(lib.mfcd_triplet_fwd_bwd_det(ptr(fs.params), ptr(fs.params[nU:]), ptr(self.store.rec),
                                                ptr(self.perm), start, b_local, fs.d, inv, fs.n, fs.m,

@@ -385,7 +385,7 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
                 if direct:
                     raise _lib.MfcdError("the wire_rle staging format is decoded by the atomic K1 only")
                 need = C.c_size_t(0)
-                check(lib.mfcd_det_workspace_bytes(Bk, fs.d, C.byref(need)), "mfcd_det_workspace_bytes")
+                check(lib.mfcd_det_workspace_bytes_nm(Bk, fs.d, fs.n, fs.m, C.byref(need)), "mfcd_det_workspace_bytes_nm")
                 ws = fs.ensure_workspace(need.value)
                 check(lib.mfcd_triplet_fwd_bwd_det(ptr(fs.params), ptr(fs.params[nU:]), ptr(src), None, 0, Bk, fs.d,
                                                    1.0 / float(gsizes[k]), fs.n, fs.m, ptr(fs.grads),

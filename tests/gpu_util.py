@@ -36,9 +36,23 @@ def fwd_bwd(U, V, store, start=0, B=None, mode="atomic", perm=None, inv_batch=No
     if mode == "atomic":
         check(lib.mfcd_triplet_fwd_bwd(ptr(Ud), ptr(Vd), ptr(store.rec), ptr(permd), start, B, d, inv, ptr(gUd),
                                        ptr(gVd), ptr(loss), current_stream()), "fwd_bwd")
-    else:
+    elif mode == "deterministic_sort":      # the sort + segmented-reduction engine under its own entry point
         need = C.c_size_t(0)
         check(lib.mfcd_det_workspace_bytes(B, d, C.byref(need)), "ws")
+        ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=DEV)
+        check(lib.mfcd_triplet_fwd_bwd_det_sort(ptr(Ud), ptr(Vd), ptr(store.rec), ptr(permd), start, B, d, inv, n, m,
+                                                ptr(gUd), ptr(gVd), ptr(loss), ptr(ws), need.value, current_stream()),
+              "fwd_bwd_det_sort")
+    elif mode == "deterministic_fixed":     # the fixed-point integer-atomic engine under its own entry point
+        need = C.c_size_t(0)
+        check(lib.mfcd_det_fixed_workspace_bytes(d, n, m, C.byref(need)), "ws")
+        ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=DEV)
+        check(lib.mfcd_triplet_fwd_bwd_det_fixed(ptr(Ud), ptr(Vd), ptr(store.rec), ptr(permd), start, B, d, inv, n, m,
+                                                 ptr(gUd), ptr(gVd), ptr(loss), ptr(ws), need.value, current_stream()),
+              "fwd_bwd_det_fixed")
+    else:                                   # default engine for this batch size
+        need = C.c_size_t(0)
+        check(lib.mfcd_det_workspace_bytes_nm(B, d, n, m, C.byref(need)), "ws")
         ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=DEV)
         check(lib.mfcd_triplet_fwd_bwd_det(ptr(Ud), ptr(Vd), ptr(store.rec), ptr(permd), start, B, d, inv, n, m,
                                            ptr(gUd), ptr(gVd), ptr(loss), ptr(ws), need.value, current_stream()),

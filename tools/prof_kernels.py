@@ -35,8 +35,27 @@ def main():
     # epoch batching + K1 atomic + K3
     loader = TripletLoader(store, B, shuffle=True, shuffle_rng="device")
     trainer.train_epoch(fs, loader, spec, 0)
-    # K2: deterministic scatter at 2^20
+    # deterministic mode at 2^20: the fixed-point engine (k_fwd_bwd_fix + k_fix_finish)
     run_epoch(fs, store.slice(0, 2 * B), None, B, spec, 1)
+    # ... and the sort engine (K2: k_seg_reduce + fix-ups after three radix sorts)
+    sub = store.slice(0, B)
+    need = C.c_size_t(0)
+    check(lib.mfcd_det_workspace_bytes(B, d, C.byref(need)), "ws")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    loss = torch.zeros(1, device=dev)
+    nU = n * d
+    check(lib.mfcd_triplet_fwd_bwd_det_sort(ptr(fs.params), ptr(fs.params[nU:]), ptr(sub.rec), None, 0, B, d, 1.0 / B, n, m,
+                                            ptr(fs.grads), ptr(fs.grads[nU:]), ptr(loss), ptr(ws), need.value,
+                                            current_stream()), "det_sort")
+    fs.grads.zero_()
+    # K9 on one rank (the rank exchanges with itself through the same flag protocol)
+    flags = torch.zeros(64, dtype=torch.int32, device=dev); counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev); other = torch.zeros_like(fs.grads)
+    arr = lambda t: (C.c_uint64 * 1)(t.data_ptr())
+    for seq in (1, 2):
+        check(lib.mfcd_dp_fused_adam_sync(arr(fs.grads), arr(fs.params), arr(flags), 0, 0, 0, 1, fs.params.numel(),
+                                          ptr(fs.state1), ptr(fs.state2), 1e-3, 0.9, 0.999, 1e-8, 1e-5, seq, seq, ptr(counter),
+                                          ptr(err), ptr(other), current_stream()), "k9")
     # K4
     eval_batches(fs, store, 64)
     # K5 + K6 on a dense block
