@@ -483,19 +483,20 @@ def main():
         traffic = facts.get("dram_bytes")
         inst = facts.get("warp_instructions")
         sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
-        config = config_dict(args, cfg, world)
-        config.update({
+        config = config_dict(args, cfg, world)          # identical to the reference arm's (same keys, same values)
+        details = {
             "dp_exchange": ("none" if world == 1 else
-                            ("peer-memory fused K9, in-kernel flags" + (" (multimem)" if dp.exchange.multimem else " (p2p)")
+                            ("peer-memory fused K9, in-kernel flags, double-buffered gradients" +
+                             (" (multimem)" if dp.exchange.multimem else " (p2p)")
                              if dp.exchange is not None else "nccl all-reduce + K3")),
             "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
             "batch_layout": ("per-epoch device shuffle; every batch grouped by user (epoch_batches.cu), inside the "
-                             "timed region" if shuffle else "store order, no reshuffle")})
+                             "timed region" if shuffle else "store order, no reshuffle")}
         line = {
             "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config,
+            "dtype": "f32", "data": "synthetic", "config": config, "run_details": details,
             "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_span (K1 fused fwd+bwd, user-grouped batches)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_triplet": bytes_per_triplet, "k1_ms": k1_ms,

@@ -12,7 +12,7 @@ f = sys.argv[1]
 try:
     lines = [l for l in open(f + ".json") if l.startswith("{")]
     d = json.loads(lines[-1]); r = d["roofline"]; e = d.get("e2e") or {}
-    print(f"{f}: value={d['value']:.4g} ms/step={d['ms_per_step']:.4f} k1_ms={r['k1_ms']:.4f} e2e={e.get('value', 0):.4g} scaling={d['scaling']} loss={d.get('final_loss')} exch={d['config'].get('dp_exchange')} clocks={d['clocks']}")
+    print(f"{f}: value={d['value']:.4g} ms/step={d['ms_per_step']:.4f} k1_ms={r['k1_ms']:.4f} e2e={e.get('value', 0):.4g} scaling={d['scaling']} loss={d.get('final_loss')} exch={(d.get('run_details') or d['config']).get('dp_exchange')} clocks={d['clocks']}")
 except Exception as ex:
     print(f, "unreadable", ex); print(open(f + ".err").read()[-2500:])
 PY
