@@ -80,6 +80,14 @@ int mfcd_unpack_triplets(const mfcd_triplet* rec, int64_t N, int64_t* u, int64_t
  * pack sets *bad (device int, caller zeroes it) if a record has a soft label or an index out of range. */
 int mfcd_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t* bad, void* stream);
 int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_triplet* out, void* stream);
+/* The same packing on the HOST's cores, for a loader that owns raw 16-byte records and feeds the GPU over PCIe:
+ * host records -> host words (both plain host pointers; `out` is normally a pinned staging buffer), split over
+ * `threads` threads of a persistent pool (<= 0: all hardware threads), AVX-512 with streaming stores where the
+ * CPU has it.  Bit-identical to mfcd_pack_triplets8.  *bad (host int, caller zeroes it) is set for soft labels
+ * or indices out of range.  Needs no GPU.  (The reference moves 28 bytes per sample per step through
+ * `x.to(device)`, structure.py:845-846.)  mfcd_host_pack_isa: 512 if the AVX-512 kernel is in use, else 0. */
+int mfcd_host_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t threads, int32_t* bad);
+int mfcd_host_pack_isa(void);
 /* Run-length wire format for ONE user-grouped batch of B hard-labelled records with n_items <= 65536
  * (4.375 bytes per triplet + 4 per run of equal users instead of 16): u32 words
  *   [n_runs, B, 0, 0 | word_run0[nw] | zbits[nw] | nbits[nw] | ij[B] | users[n_runs]],  nw = ceil(B/32);

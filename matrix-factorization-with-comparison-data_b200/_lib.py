@@ -60,6 +60,8 @@ SIGNATURES = {
     "mfcd_unpack_triplets": [P, I64, P, P, P, P, P],
     "mfcd_pack_triplets8": [P, I64, P, P, P],
     "mfcd_unpack_triplets8": [P, I64, P, P],
+    "mfcd_host_pack_triplets8": [P, I64, P, I32, P],
+    "mfcd_host_pack_isa": [],
     "mfcd_wire_layout": [I64, C.POINTER(I64), C.POINTER(I64), C.POINTER(SZ)],
     "mfcd_pack_wire": [P, I64, P, I64, P, P, SZ, P],
     "mfcd_unpack_wire": [P, I64, P, P],

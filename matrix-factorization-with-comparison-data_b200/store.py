@@ -444,30 +444,46 @@ class HostTripletLoader:
       "records16"  (B, 4) int32 records as they sit in HBM                                16 B / triplet
       "wire8"      uint64 hard-label records, unpacked by mfcd_unpack_triplets8             8 B / triplet
       "wire_rle"   run-length words of a user-grouped batch, decoded by K1 itself        ~4.5 B / triplet
+      "wire8_live" the host keeps RAW 16-byte records (pinned or not); every step the batch is packed to the
+                   8-byte format by the library's own host threads (mfcd_host_pack_triplets8, csrc/host_pack.cpp)
+                   into a ring of pinned staging buffers while the previous batches are in flight   8 B / triplet
+                   over PCIe, nothing prepared beforehand.  pack_threads: host threads of the packer (default:
+                   the host's cores divided by the ranks on this host, at most 16).
     """
 
-    def __init__(self, batches, sizes, fmt="records16", user_grouped=False):
-        assert fmt in ("records16", "wire8", "wire_rle")
+    def __init__(self, batches, sizes, fmt="records16", user_grouped=False, pack_threads=None):
+        assert fmt in ("records16", "wire8", "wire_rle", "wire8_live")
         assert len(batches) == len(sizes)
         for b in batches:
-            if not (isinstance(b, torch.Tensor) and b.device.type == "cpu" and b.is_pinned() and b.is_contiguous()):
+            if not (isinstance(b, torch.Tensor) and b.device.type == "cpu" and b.is_contiguous()
+                    and (b.is_pinned() or fmt == "wire8_live")):
                 raise ValueError("HostTripletLoader needs contiguous PINNED host tensors (torch.Tensor.pin_memory())")
         self.batches, self.sizes, self.fmt = list(batches), [int(x) for x in sizes], fmt
+        if pack_threads is None:
+            import os
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            pack_threads = max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
+        self.pack_threads = int(pack_threads)
         self.user_grouped = bool(user_grouped) or fmt == "wire_rle"
         self.batch_size = max(self.sizes) if self.sizes else 0
         self.shuffle = False
         self.dataset = None
 
     @classmethod
-    def from_records(cls, rec, batch_size, fmt="records16", user_grouped=False):
+    def from_records(cls, rec, batch_size, fmt="records16", user_grouped=False, pack_threads=None):
         """rec: (N, 4) int32 records (numpy or CPU tensor), cut into batches of batch_size in order.
-        wire8 / wire_rle are packed here on the host (hostpack.py); wire_rle groups every batch by user first."""
+        wire8 / wire_rle are packed here on the host (hostpack.py); wire_rle groups every batch by user first;
+        wire8_live keeps the raw records and packs them step by step while training."""
         import numpy as np
         from . import hostpack
         a = rec.numpy() if isinstance(rec, torch.Tensor) else np.asarray(rec)
         assert a.ndim == 2 and a.shape[1] == 4 and a.dtype == np.int32
         N, B = a.shape[0], int(batch_size)
         sizes = [min(B, N - s0) for s0 in range(0, N, B)]
+        if fmt == "wire8_live":
+            host = rec if isinstance(rec, torch.Tensor) and rec.is_contiguous() else \
+                torch.from_numpy(np.ascontiguousarray(a))
+            return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped, pack_threads)
         if fmt == "records16":
             host = torch.empty((N, 4), dtype=torch.int32).pin_memory()
             host.copy_(torch.from_numpy(np.ascontiguousarray(a)))
@@ -493,6 +509,9 @@ class HostTripletLoader:
         return sum(self.sizes)
 
     def bytes_per_step(self):
+        """bytes that cross PCIe per optimiser step (mean over the batches)"""
+        if self.fmt == "wire8_live":
+            return 8.0 * sum(self.sizes) / max(len(self.sizes), 1)
         return sum(b.numel() * b.element_size() for b in self.batches) / max(len(self.batches), 1)
 
     def begin_iteration(self):

@@ -312,8 +312,15 @@ class _Stager:
         self.rec = [torch.empty((B, 4), dtype=torch.int32, device=dev) for _ in range(2)] \
             if loader.fmt != "wire_rle" else [None, None]
         self.raw = None
-        if loader.fmt == "wire8":
+        self.live = loader.fmt == "wire8_live"
+        if loader.fmt in ("wire8", "wire8_live"):
             self.raw = [torch.empty(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        if self.live:
+            # the packer's ring: slot k % 3 is packed (host threads) -> copied (DMA) -> free again
+            from concurrent.futures import ThreadPoolExecutor
+            self.hpk = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(3)]
+            self.copied = [torch.cuda.Event() for _ in range(3)]
+            self.packer = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mfcd-pack")
         elif loader.fmt == "wire_rle":
             cap = max(b.numel() for b in loader.batches)
             self.raw = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
@@ -350,27 +357,54 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
 
+        packed = {}
+
+        def pack(k):
+            # worker thread: raw records of batch k -> 8-byte words in pinned slot k % 3, once the DMA that last
+            # read that slot (batch k - 3) has finished; the C call releases the GIL and fans out over host threads
+            s, h = k % 3, loader.batches[k]
+            st.copied[s].synchronize()
+            bad = C.c_int32(0)
+            check(lib.mfcd_host_pack_triplets8(h.data_ptr(), loader.sizes[k], st.hpk[s].data_ptr(),
+                                               loader.pack_threads, C.byref(bad)), "mfcd_host_pack_triplets8")
+            if bad.value:
+                raise _lib.MfcdError("wire8_live: soft labels or indices beyond 2^23 users / 2^20 items do not fit "
+                                     "the 8-byte staging format (use fmt='records16')")
+
+        def submit_pack(k):
+            if st.live and k < n_steps:
+                packed[k] = st.packer.submit(pack, k)
+
         def upload(k):
             b = k % 2
+            if st.live:
+                packed.pop(k).result()
             with torch.cuda.stream(st.copy_stream):
                 st.copy_stream.wait_event(st.freed[b])
                 h = loader.batches[k]
                 if loader.fmt == "records16":
                     st.rec[b][: h.shape[0]].copy_(h, non_blocking=True)
                 else:
-                    st.raw[b][: h.numel()].copy_(h, non_blocking=True)
-                    if loader.fmt == "wire8":
+                    if st.live:
+                        st.raw[b][: loader.sizes[k]].copy_(st.hpk[k % 3][: loader.sizes[k]], non_blocking=True)
+                        st.copied[k % 3].record(st.copy_stream)
+                    else:
+                        st.raw[b][: h.numel()].copy_(h, non_blocking=True)
+                    if loader.fmt != "wire_rle":
                         check(lib.mfcd_unpack_triplets8(ptr(st.raw[b]), loader.sizes[k], ptr(st.rec[b]),
                                                         st.copy_stream.cuda_stream), "mfcd_unpack_triplets8")
                 st.ready[b].record(st.copy_stream)
+            submit_pack(k + 3)                       # its slot is the one this copy frees
 
         for b in range(2):
             st.freed[b].record(main)
+        for k in range(3):
+            submit_pack(k)
         if n_steps:
             upload(0)
         pending = None
         for k in range(n_steps):
-            if k + 1 < n_steps:
+            if k + 1 < n_steps and not st.live:
                 upload(k + 1)
             b = k % 2
             main.wait_event(st.ready[b])
@@ -393,6 +427,8 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
                                                    ws.numel() if ws is not None else 0, main.cuda_stream),
                       "mfcd_triplet_fwd_bwd_det")
             st.freed[b].record(main)
+            if k + 1 < n_steps and st.live:
+                upload(k + 1)                        # waits for the packer: after this step's K1 is queued
             step = fs.step + 1
             if dp is not None and dp.exchange is not None:
                 dp.exchange.step(fs, spec, step)

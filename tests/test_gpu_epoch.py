@@ -151,7 +151,7 @@ def test_train_model_large_batch_equals_the_oracle_on_the_reshuffled_epochs(G, r
     assert abs(v_losses[-1] - O.mean_of_batch_means(Uo, Vo, vb)) < 1e-5
 
 
-@pytest.mark.parametrize("fmt", ["records16", "wire8", "wire_rle"])
+@pytest.mark.parametrize("fmt", ["records16", "wire8", "wire_rle", "wire8_live"])
 def test_host_resident_loader_streams_batches_and_matches_the_oracle(G, fmt):
     """train_model over a HostTripletLoader (pinned host batches, one H2D copy per step, loss read back per step):
     same steps as the oracle; the host packers are bit-identical to the device packers."""

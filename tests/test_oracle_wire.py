@@ -64,3 +64,50 @@ def test_product_host_packers_match_the_oracle(N, n):
         hostpack.pack_wire(soft)
     with pytest.raises(ValueError):
         hostpack.pack8(soft)
+
+
+def _pack8_by_the_book(u, i, j, z):
+    """include/mfcd_b200.h: bit 0 = label, [1,21) = j, [21,41) = i, [41,64) = u -- restated with python ints"""
+    return np.array([(int(a) << 41) | (int(b) << 21) | (int(c) << 1) | int(l != 0) for a, b, c, l in zip(u, i, j, z)],
+                    dtype=np.uint64)
+
+
+@pytest.mark.parametrize("N", [0, 1, 7, 8, 9, 63, 4097, (1 << 17) + 3])
+@pytest.mark.parametrize("threads", [1, 3, 0])
+def test_c_host_packer_matches_the_layout(N, threads):
+    """mfcd_host_pack_triplets8 (csrc/host_pack.cpp: thread pool + AVX-512 / scalar kernels; needs no GPU) against
+    the header's bit layout: ragged sizes around the 8-record vector width, unaligned outputs, extreme indices,
+    -0.0 labels, and the `bad` flag for soft labels / indices beyond the format."""
+    import ctypes as C
+    from mfcd_b200 import _lib, hostpack
+    rng = np.random.default_rng(N + 17)
+    u, i, j = rng.integers(0, 1 << 23, N), rng.integers(0, 1 << 20, N), rng.integers(0, 1 << 20, N)
+    z = rng.integers(0, 2, N).astype(np.float64)
+    if N > 2:
+        u[0], i[0], j[0], z[0] = (1 << 23) - 1, (1 << 20) - 1, (1 << 20) - 1, 1.0
+        u[1], i[1], j[1] = 0, 0, 0
+    rec = hostpack.as_records(u, i, j, z)
+    if N > 2:
+        rec[1, 3] = np.float32(-0.0).view(np.int32)                         # -0.0 is label 0
+        z[1] = 0.0
+    want = _pack8_by_the_book(u, i, j, z)
+    for shift in (0, 1):                                                     # 64-byte aligned or not
+        buf = np.zeros(N + 9, np.uint64)
+        off = (-(buf.ctypes.data // 8)) % 8 + shift
+        out = buf[off:off + N]
+        bad = C.c_int32(0)
+        rc = _lib.lib.mfcd_host_pack_triplets8(rec.ctypes.data, N, out.ctypes.data, threads, C.byref(bad))
+        assert rc == 0 and bad.value == 0
+        assert np.array_equal(out, want)
+        assert buf[:off].sum() == 0 and buf[off + N:].sum() == 0            # nothing written outside
+    if N:
+        assert np.array_equal(want, hostpack.pack8(rec))
+    for col, val in ((0, 1 << 23), (0, -1), (1, 1 << 20), (2, 1 << 20), (3, int(np.float32(0.5).view(np.int32))),
+                     (3, int(np.float32(2.0).view(np.int32)))):
+        for pos in {0, N // 2, N - 1} if N else ():
+            r = rec.copy(); r[pos, col] = val
+            bad = C.c_int32(0)
+            out = np.zeros(N, np.uint64)
+            assert _lib.lib.mfcd_host_pack_triplets8(r.ctypes.data, N, out.ctypes.data, threads, C.byref(bad)) == 0
+            assert bad.value == 1, (col, val, pos)
+    assert _lib.lib.mfcd_host_pack_triplets8(None, 5, None, 1, None) == -1                 # MFCD_ERR_ARG

@@ -17,8 +17,15 @@ ap.add_argument("--p", type=float, default=0.1)
 ap.add_argument("--ds", default="2,8,32,128"); ap.add_argument("--strategies", default="random,margin,svd,popularity")
 ap.add_argument("--epochs", type=int, default=10); ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--lr", type=float, default=1e-2)
+ap.add_argument("--wd", type=float, default=None,
+                help="weight decay; default 1e-5 * 64 / batch: the reference's coupled L2 (1e-5 at batch 64) acts on a "
+                     "batch-MEAN gradient, so at batch 65536 an unscaled 1e-5 outweighs the per-row data gradient "
+                     "(~1e-5 |V|) and every uniform-item run collapses to U = V = 0 (loss ln 2) -- plain torch on the "
+                     "CPU does the same, tools/config5_dynamics_cpu.py")
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config5.json"))
 a = ap.parse_args()
+if a.wd is None:
+    a.wd = 1e-5 * 64.0 / a.batch
 
 FUNCS = ("generate_X", "split_dataset_from_triplets", "evaluate_model", "compute_reconstruction_error",
          "compute_alpha_and_norm_ratios", "compute_ground_truth_metrics")
@@ -47,7 +54,7 @@ for strategy in a.strategies.split(","):
         store.clear()
         torch.cuda.synchronize(); t0 = time.perf_counter()
         try:
-            out = structure.run_experiment(a.n, a.m, d, a.p, 1.0, "cuda", a.lr, 1e-5, reps=1, num_epochs=a.epochs,
+            out = structure.run_experiment(a.n, a.m, d, a.p, 1.0, "cuda", a.lr, a.wd, reps=1, num_epochs=a.epochs,
                                            K=1, strategy=strategy, batch_size=a.batch)
             torch.cuda.synchronize(); total = time.perf_counter() - t0
             n_train = int(0.8 * int(a.n * a.m * a.p / 2))
