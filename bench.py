@@ -405,7 +405,6 @@ def main():
                                 for f, v in e2e_formats.items() if f != head}
         if "wire8_live" in e2e_formats:
             # the packer alone, same threads, one batch: what bounds wire8_live when the host is the slow side
-            import ctypes as C
             from mfcd_b200 import _lib
             dst = torch.empty(B, dtype=torch.int64).pin_memory()
             badf = C.c_int32(0)

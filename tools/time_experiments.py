@@ -6,13 +6,15 @@ import numpy as np, torch
 import structure
 
 def timed(fn_name, store):
-    orig = getattr(structure, fn_name)
+    # run_experiment calls the trainer's train_model directly; everything else through the module's own names
+    mod = structure._trainer if fn_name == "train_model" else structure
+    orig = getattr(mod, fn_name)
     def wrap(*a, **k):
         torch.cuda.synchronize(); t = time.perf_counter()
         out = orig(*a, **k)
         torch.cuda.synchronize(); store[fn_name] = store.get(fn_name, 0.0) + time.perf_counter() - t
         return out
-    setattr(structure, fn_name, wrap)
+    setattr(mod, fn_name, wrap)
     return orig
 
 res = {}
@@ -28,7 +30,7 @@ for tag, (n, m, d, p, s, K, epochs) in {"c1": (100, 100, 2, 0.1, 1.0, 1, 30), "c
     torch.cuda.synchronize(); t0 = time.perf_counter()
     out = structure.run_experiment(n, m, d, p, s, "cuda", 1e-3, 1e-5, reps=1, num_epochs=epochs, K=K)
     torch.cuda.synchronize(); total = time.perf_counter() - t0
-    for f, o in origs.items(): setattr(structure, f, o)
+    for f, o in origs.items(): setattr(structure._trainer if f == "train_model" else structure, f, o)
     n_train = int(0.8 * int(n * m * p / 2)) * K
     res[tag] = {"config": dict(n=n, m=m, d=d, p=p, K=K, epochs=epochs), "total_s": total, "breakdown_s": store,
                 "train_samples_per_epoch": n_train, "steps_per_epoch": (n_train + 63) // 64,
