@@ -356,6 +356,7 @@ def main():
             hl = HostTripletLoader.from_records(host_rec, B, fmt=fmt)
             pack_times[fmt] = time.perf_counter() - t0
             hl.hot = hot
+            hl.prepare(dev)                 # staging slots / pinned ring: once per loader, like its pinned batches
             warm = HostTripletLoader(hl.batches[:max(W, 1)], hl.sizes[:max(W, 1)], fmt=fmt, user_grouped=hl.user_grouped)
             warm.hot = hot
             # the staging code has just WRITTEN the pinned batches with the CPU: the last ones are still dirty in
@@ -396,9 +397,9 @@ def main():
                       "it; the device unpacks with one kernel.  Then K1 -> exchange -> Adam -> the step's loss copied back "
                       "and read by the host every step (one step behind the launches); wall clock, max over ranks.  The "
                       "headline is the faster of these two.  other_formats: the rest, incl. batches the HOST packed "
-                      "BEFOREHAND (hostpack.py, numpy) -- wire8 = 8-byte records, wire_rle = run-length words of "
-                      "user-grouped batches decoded by K1; their packing is NOT in the timed region and costs "
-                      "host_pack_s_per_epoch on one core (pack-once, stream-every-epoch formats)"
+                      "BEFOREHAND -- wire8 = 8-byte records (same C packer, all host threads), wire_rle = run-length "
+                      "words of user-grouped batches decoded by K1 (hostpack.py, numpy, one core); their packing is NOT "
+                      "in the timed region and costs host_pack_s_per_epoch (pack-once, stream-every-epoch formats)"
                       % HostTripletLoader([], [], fmt="wire8_live").pack_threads)
         e2e["other_formats"] = {f: {"value": v["value"], "h2d_bytes_per_step": v["h2d_bytes_per_step"],
                                     "host_pack_s_per_epoch": (0.0 if f in ("records16", "wire8_live") else pack_times[f])}

@@ -489,8 +489,16 @@ class HostTripletLoader:
             host.copy_(torch.from_numpy(np.ascontiguousarray(a)))
             return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped)
         if fmt == "wire8":
+            # packed once, here, by the library's host threads (csrc/host_pack.cpp; same bits as hostpack.pack8)
+            import ctypes as C
+            from ._lib import lib, check
             host = torch.empty(N, dtype=torch.int64).pin_memory()
-            host.copy_(torch.from_numpy(hostpack.pack8(a).view(np.int64)))
+            src = np.ascontiguousarray(a)
+            bad = C.c_int32(0)
+            check(lib.mfcd_host_pack_triplets8(src.ctypes.data, N, host.data_ptr(), 0, C.byref(bad)),
+                  "mfcd_host_pack_triplets8")
+            if bad.value:
+                raise ValueError("pack8: soft labels or indices beyond 2^23 users / 2^20 items do not fit the 8-byte format")
             return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped)
         words = [hostpack.pack_wire(a[s0:s0 + B] if user_grouped else hostpack.group_by_user(a[s0:s0 + B]))
                  for s0 in range(0, N, B)]
@@ -516,6 +524,13 @@ class HostTripletLoader:
 
     def begin_iteration(self):
         return None
+
+    def prepare(self, device=None):
+        """Allocate the per-loader staging state now (device slots, copy stream, and for wire8_live the ring of
+        pinned buffers + the packer thread) instead of at the first epoch.  Optional; returns self."""
+        from . import trainer
+        trainer.stager_for(self, compute_device(device))
+        return self
 
 
 def as_loader(loader, device=None) -> TripletLoader:

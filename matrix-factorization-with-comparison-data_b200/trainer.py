@@ -330,6 +330,14 @@ class _Stager:
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
 
 
+def stager_for(loader: HostTripletLoader, dev) -> _Stager:
+    st = loader.__dict__.get("_stager")
+    if st is None or st.dev != torch.device(dev):
+        with torch.cuda.device(dev):
+            st = loader._stager = _Stager(loader, torch.device(dev))
+    return st
+
+
 def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec, scatter, dp=None, hot=None):
     """One epoch over a HOST-resident loader: per optimiser step the batch is copied host -> device from pinned
     memory on a copy stream (double-buffered: the copy of batch k+1 overlaps the step on batch k), K1 runs on the
@@ -337,9 +345,7 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
     exchange, and the step's loss is copied back and READ BY THE HOST every step (one step behind the launches, so
     the GPU never waits for python).  Returns the per-step losses as a python list."""
     dev = fs.params.device
-    st = loader.__dict__.get("_stager")
-    if st is None or st.dev != dev:
-        st = loader._stager = _Stager(loader, dev)
+    st = stager_for(loader, dev)
     n_steps = len(loader)
     world = dp.world if dp is not None else 1
     sizes = torch.tensor(loader.sizes, dtype=torch.int64, device=dev)
