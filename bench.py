@@ -304,7 +304,11 @@ def main():
     if warm_loader is not None:
         trainer.train_epoch(fs, warm_loader, spec, mode, dp=dp)
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank) if rank == 0 else None     # NVML init happens BEFORE the barrier (it takes ms)
+    nvml_index = local_rank                          # NVML ignores CUDA_VISIBLE_DEVICES: map the CUDA ordinal back
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    if vis and all(t.strip().isdigit() for t in vis.split(",")) and local_rank < len(vis.split(",")):
+        nvml_index = int(vis.split(",")[local_rank])
+    clocks = ClockSampler(nvml_index) if rank == 0 else None     # NVML init happens BEFORE the barrier (it takes ms)
     barrier()
     barrier()
     check(lib.mfcd_profile_k1(1), "profile")

@@ -462,7 +462,8 @@ class HostTripletLoader:
         if pack_threads is None:
             import os
             local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-            pack_threads = max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
+            pack_threads = int(os.environ.get("MFCD_PACK_THREADS", "0") or 0) or \
+                max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
         self.pack_threads = int(pack_threads)
         self.user_grouped = bool(user_grouped) or fmt == "wire_rle"
         self.batch_size = max(self.sizes) if self.sizes else 0
