@@ -518,12 +518,22 @@ def main():
             "hot_item_rows_privatised": (hot[1].numel() if hot else 0),
             "batch_layout": ("per-epoch device shuffle; every batch grouped by user (epoch_batches.cu), inside the "
                              "timed region" if shuffle else "store order, no reshuffle")}
+        # which K1 the dispatch picks for this run (k1_lean.cuh::launch_lean, triplet_fwd_bwd.cu)
+        if mode == 1:
+            k1_name = ("k_fwd_bwd_fix + k_fix_finish (deterministic, fixed-point integer atomics)" if B <= 16384 else
+                       "k_fwd_bwd (MODE 1) + radix sorts + k_seg_reduce (deterministic, sort engine)")
+        elif d % 4 == 0 and d >= 64 and d in (64, 128, 256, 384, 512) and shuffle:
+            k1_name = "k_fwd_bwd_span (K1 fused fwd+bwd, user-grouped batches, d >= 64)"
+        elif d % 4 == 0 and d in (4, 8, 16, 32):
+            k1_name = "k_fwd_bwd_lean (K1 fused fwd+bwd, user runs)" if shuffle else "k_fwd_bwd_lean (K1 fused fwd+bwd)"
+        else:
+            k1_name = "k_fwd_bwd_lean / k_fwd_bwd (K1 fused fwd+bwd)"
         line = {
             "metric": "triplets_per_sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": (wall1 - wall0) * 1e3 / K,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config, "run_details": details,
-            "roofline": {"bound": "hbm", "kernel": "k_fwd_bwd_span (K1 fused fwd+bwd, user-grouped batches)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_triplet": bytes_per_triplet, "k1_ms": k1_ms,
                          "dram_frac": (traffic / (k1_ms * 1e-3) / 1e9 / peak) if traffic else None,

@@ -448,10 +448,14 @@ class HostTripletLoader:
                    8-byte format by the library's own host threads (mfcd_host_pack_triplets8, csrc/host_pack.cpp)
                    into a ring of pinned staging buffers while the previous batches are in flight   8 B / triplet
                    over PCIe, nothing prepared beforehand.  pack_threads: host threads of the packer (default:
-                   the host's cores divided by the ranks on this host, at most 16).
+                   the host's cores divided by the ranks on this host, at most 16).  pack_fraction f in (0, 1]:
+                   only the first f of every batch is packed, the rest travels as raw records in the same step
+                   (needs pinned batches) -- the packer and the PCIe link then work side by side instead of the
+                   packer alone setting the pace; "auto" (prepare() measures the packer and the link once and
+                   balances them); default 1.0, env MFCD_PACK_FRACTION.
     """
 
-    def __init__(self, batches, sizes, fmt="records16", user_grouped=False, pack_threads=None):
+    def __init__(self, batches, sizes, fmt="records16", user_grouped=False, pack_threads=None, pack_fraction=None):
         assert fmt in ("records16", "wire8", "wire_rle", "wire8_live")
         assert len(batches) == len(sizes)
         for b in batches:
@@ -465,13 +469,25 @@ class HostTripletLoader:
             pack_threads = int(os.environ.get("MFCD_PACK_THREADS", "0") or 0) or \
                 max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
         self.pack_threads = int(pack_threads)
+        if pack_fraction is None:
+            import os
+            pack_fraction = os.environ.get("MFCD_PACK_FRACTION", "1.0") or "1.0"
+        if isinstance(pack_fraction, str) and pack_fraction != "auto":
+            pack_fraction = float(pack_fraction)
+        if pack_fraction != "auto" and not (0.0 < float(pack_fraction) <= 1.0):
+            raise ValueError("pack_fraction must be in (0, 1] or 'auto'")
+        self.pack_fraction = pack_fraction
+        if fmt == "wire8_live" and pack_fraction != 1.0 and not all(b.is_pinned() for b in batches):
+            raise ValueError("wire8_live with pack_fraction < 1 ships part of every batch raw: the batches must be "
+                             "pinned (from_records pins them)")
         self.user_grouped = bool(user_grouped) or fmt == "wire_rle"
         self.batch_size = max(self.sizes) if self.sizes else 0
         self.shuffle = False
         self.dataset = None
 
     @classmethod
-    def from_records(cls, rec, batch_size, fmt="records16", user_grouped=False, pack_threads=None):
+    def from_records(cls, rec, batch_size, fmt="records16", user_grouped=False, pack_threads=None,
+                     pack_fraction=None):
         """rec: (N, 4) int32 records (numpy or CPU tensor), cut into batches of batch_size in order.
         wire8 / wire_rle are packed here on the host (hostpack.py); wire_rle groups every batch by user first;
         wire8_live keeps the raw records and packs them step by step while training."""
@@ -482,9 +498,15 @@ class HostTripletLoader:
         N, B = a.shape[0], int(batch_size)
         sizes = [min(B, N - s0) for s0 in range(0, N, B)]
         if fmt == "wire8_live":
-            host = rec if isinstance(rec, torch.Tensor) and rec.is_contiguous() else \
-                torch.from_numpy(np.ascontiguousarray(a))
-            return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped, pack_threads)
+            import os
+            pf = pack_fraction if pack_fraction is not None else (os.environ.get("MFCD_PACK_FRACTION", "1.0") or "1.0")
+            if pf in (1.0, "1.0", "1"):
+                host = rec if isinstance(rec, torch.Tensor) and rec.is_contiguous() else \
+                    torch.from_numpy(np.ascontiguousarray(a))
+            else:                                   # part of every batch travels raw: pinned, like records16
+                host = torch.empty((N, 4), dtype=torch.int32).pin_memory()
+                host.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+            return cls([host[s0:s0 + B] for s0 in range(0, N, B)], sizes, fmt, user_grouped, pack_threads, pf)
         if fmt == "records16":
             host = torch.empty((N, 4), dtype=torch.int32).pin_memory()
             host.copy_(torch.from_numpy(np.ascontiguousarray(a)))
@@ -520,7 +542,8 @@ class HostTripletLoader:
     def bytes_per_step(self):
         """bytes that cross PCIe per optimiser step (mean over the batches)"""
         if self.fmt == "wire8_live":
-            return 8.0 * sum(self.sizes) / max(len(self.sizes), 1)
+            f = self.pack_fraction if self.pack_fraction != "auto" else getattr(self, "_auto_fraction", 1.0)
+            return (8.0 * f + 16.0 * (1.0 - f)) * sum(self.sizes) / max(len(self.sizes), 1)
         return sum(b.numel() * b.element_size() for b in self.batches) / max(len(self.batches), 1)
 
     def begin_iteration(self):

@@ -321,6 +321,8 @@ class _Stager:
             self.hpk = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(3)]
             self.copied = [torch.cuda.Event() for _ in range(3)]
             self.packer = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mfcd-pack")
+            self.fraction = self._balance(loader) if loader.pack_fraction == "auto" else float(loader.pack_fraction)
+            loader._auto_fraction = self.fraction
         elif loader.fmt == "wire_rle":
             cap = max(b.numel() for b in loader.batches)
             self.raw = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
@@ -328,6 +330,35 @@ class _Stager:
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.freed = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
+
+
+def _stager_balance(self, loader):
+    """pack_fraction='auto': time the packer on one whole batch (Tp) and the link on one raw batch (Tc), both
+    alone; with a fraction f packed the packer needs f Tp and the link (1 - f / 2) Tc per step -> f = Tc / (Tp + Tc / 2)."""
+    import time
+    B = loader.batch_size
+    if not loader.batches or B < 1:
+        return 1.0
+    src = loader.batches[0]
+    n = int(loader.sizes[0])
+    bad = C.c_int32(0)
+    tp = tc = float("inf")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        t0 = time.perf_counter()
+        check(lib.mfcd_host_pack_triplets8(src.data_ptr(), n, self.hpk[0].data_ptr(), loader.pack_threads,
+                                           C.byref(bad)), "mfcd_host_pack_triplets8")
+        tp = min(tp, time.perf_counter() - t0)
+        a.record()
+        self.rec[0][:n].copy_(src[:n], non_blocking=True)
+        b.record()
+        b.synchronize()
+        tc = min(tc, a.elapsed_time(b) * 1e-3)
+    f = tc / (tp + 0.5 * tc)
+    return float(min(1.0, max(0.05, f)))
+
+
+_Stager._balance = _stager_balance
 
 
 def stager_for(loader: HostTripletLoader, dev) -> _Stager:
@@ -371,11 +402,15 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
             s, h = k % 3, loader.batches[k]
             st.copied[s].synchronize()
             bad = C.c_int32(0)
-            check(lib.mfcd_host_pack_triplets8(h.data_ptr(), loader.sizes[k], st.hpk[s].data_ptr(),
+            check(lib.mfcd_host_pack_triplets8(h.data_ptr(), n_packed(k), st.hpk[s].data_ptr(),
                                                loader.pack_threads, C.byref(bad)), "mfcd_host_pack_triplets8")
             if bad.value:
                 raise _lib.MfcdError("wire8_live: soft labels or indices beyond 2^23 users / 2^20 items do not fit "
                                      "the 8-byte staging format (use fmt='records16')")
+
+        def n_packed(k):
+            # records of batch k that travel packed (the first ones; the rest goes raw in the same step)
+            return loader.sizes[k] if st.fraction >= 1.0 else max(1, int(loader.sizes[k] * st.fraction))
 
         def submit_pack(k):
             if st.live and k < n_steps:
@@ -383,20 +418,23 @@ def stream_epoch(fs: _FlatState, loader: HostTripletLoader, spec: OptimizerSpec,
 
         def upload(k):
             b = k % 2
-            if st.live:
-                packed.pop(k).result()
             with torch.cuda.stream(st.copy_stream):
                 st.copy_stream.wait_event(st.freed[b])
                 h = loader.batches[k]
                 if loader.fmt == "records16":
                     st.rec[b][: h.shape[0]].copy_(h, non_blocking=True)
+                elif st.live:
+                    n8, nk = n_packed(k), loader.sizes[k]
+                    if n8 < nk:                      # the raw tail needs nothing from the packer: it goes first
+                        st.rec[b][n8:nk].copy_(h[n8:nk], non_blocking=True)
+                    packed.pop(k).result()
+                    st.raw[b][:n8].copy_(st.hpk[k % 3][:n8], non_blocking=True)
+                    st.copied[k % 3].record(st.copy_stream)
+                    check(lib.mfcd_unpack_triplets8(ptr(st.raw[b]), n8, ptr(st.rec[b]),
+                                                    st.copy_stream.cuda_stream), "mfcd_unpack_triplets8")
                 else:
-                    if st.live:
-                        st.raw[b][: loader.sizes[k]].copy_(st.hpk[k % 3][: loader.sizes[k]], non_blocking=True)
-                        st.copied[k % 3].record(st.copy_stream)
-                    else:
-                        st.raw[b][: h.numel()].copy_(h, non_blocking=True)
-                    if loader.fmt != "wire_rle":
+                    st.raw[b][: h.numel()].copy_(h, non_blocking=True)
+                    if loader.fmt == "wire8":
                         check(lib.mfcd_unpack_triplets8(ptr(st.raw[b]), loader.sizes[k], ptr(st.rec[b]),
                                                         st.copy_stream.cuda_stream), "mfcd_unpack_triplets8")
                 st.ready[b].record(st.copy_stream)

@@ -151,7 +151,7 @@ def test_train_model_large_batch_equals_the_oracle_on_the_reshuffled_epochs(G, r
     assert abs(v_losses[-1] - O.mean_of_batch_means(Uo, Vo, vb)) < 1e-5
 
 
-@pytest.mark.parametrize("fmt", ["records16", "wire8", "wire_rle", "wire8_live"])
+@pytest.mark.parametrize("fmt", ["records16", "wire8", "wire_rle", "wire8_live", "wire8_live:0.4", "wire8_live:auto"])
 def test_host_resident_loader_streams_batches_and_matches_the_oracle(G, fmt):
     """train_model over a HostTripletLoader (pinned host batches, one H2D copy per step, loss read back per step):
     same steps as the oracle; the host packers are bit-identical to the device packers."""
@@ -163,7 +163,8 @@ def test_host_resident_loader_streams_batches_and_matches_the_oracle(G, fmt):
     u, i, j = rng.integers(0, n, N), rng.integers(0, m, N), rng.integers(0, m, N)
     z = rng.integers(0, 2, N).astype(np.float64)
     rec = hostpack.as_records(u, i, j, z)
-    hl = HostTripletLoader.from_records(rec, B, fmt=fmt)
+    fmt, _, frac = fmt.partition(":")            # wire8_live:f = only a fraction f of every batch is packed
+    hl = HostTripletLoader.from_records(rec, B, fmt=fmt, pack_fraction=(frac or None) if frac in ("", "auto") else float(frac))
     assert len(hl) == 5 and hl.n_samples() == N and hl.sizes[-1] == 123
     # host packers == device packers, bit for bit
     dstore = G.store_from(u[:B], i[:B], j[:B], z[:B])
