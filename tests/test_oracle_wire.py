@@ -111,3 +111,39 @@ def test_c_host_packer_matches_the_layout(N, threads):
             assert _lib.lib.mfcd_host_pack_triplets8(r.ctypes.data, N, out.ctypes.data, threads, C.byref(bad)) == 0
             assert bad.value == 1, (col, val, pos)
     assert _lib.lib.mfcd_host_pack_triplets8(None, 5, None, 1, None) == -1                 # MFCD_ERR_ARG
+
+
+def test_c_host_packer_pool_under_concurrent_callers():
+    """The packer's thread pool is shared by every caller in the process (the streaming epoch calls it from a worker
+    thread while benchmarks / other loaders may call it too): concurrent calls with different thread counts must
+    neither deadlock nor mix their chunks."""
+    import ctypes as C
+    import threading
+    from mfcd_b200 import _lib, hostpack
+    N = 150_001                                                   # > 2 chunks of 32768: the pool path
+    recs, refs = [], []
+    for seed in range(4):
+        r = np.random.default_rng(seed)
+        rec = hostpack.as_records(r.integers(0, 1 << 23, N), r.integers(0, 1 << 20, N), r.integers(0, 1 << 20, N),
+                                  r.integers(0, 2, N).astype(np.float64))
+        recs.append(rec)
+        refs.append(hostpack.pack8(rec))
+    errors = []
+
+    def caller(w):
+        out = np.zeros(N, np.uint64)
+        bad = C.c_int32(0)
+        for it in range(60):
+            k, threads = (w + it) % 4, (1, 2, 5, 16, 0)[(it + w) % 5]
+            rc = _lib.lib.mfcd_host_pack_triplets8(recs[k].ctypes.data, N, out.ctypes.data, threads, C.byref(bad))
+            if rc or bad.value or not np.array_equal(out, refs[k]):
+                errors.append((w, it, rc, bad.value))
+                return
+
+    ts = [threading.Thread(target=caller, args=(w,), daemon=True) for w in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts), "packer pool deadlocked"
+    assert not errors, errors[:3]
