@@ -8,9 +8,11 @@ can ship them as they are (16-byte records) or pack them first:
                (decoded by K1 itself, MFCD_FLAG_WIRE_RLE; mfcd_unpack_wire for other consumers)
 
 These are the CPU counterparts of mfcd_pack_triplets8 / mfcd_pack_wire (bit-identical output, checked by the GPU
-tests).  They run at numpy speed (~1e8 triplets/s per core): a host can pack a dataset ONCE and stream the packed
-batches every epoch, it cannot pack at the rate the GPU trains -- bench.py reports the packing time next to the
-end-to-end numbers of the packed formats.
+tests).  They run at numpy speed (~1e8 triplets/s per core) and are the readable statement of the formats; the
+loaders themselves pack the 8-byte format with the library's C packer (mfcd_host_pack_triplets8, csrc/host_pack.cpp:
+thread pool + AVX-512, ~3e9 triplets/s on 16 threads -- fast enough to pack every batch inside the step loop,
+HostTripletLoader fmt="wire8_live").  pack_wire has no C twin: a host packs that format once and streams it every
+epoch; bench.py reports the packing time next to the end-to-end numbers of the packed formats.
 """
 from __future__ import annotations
 
