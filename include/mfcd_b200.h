@@ -85,7 +85,8 @@ int mfcd_unpack_triplets8(const uint64_t* packed, int64_t N, mfcd_triplet* out, 
  * `threads` threads of a persistent pool (<= 0: all hardware threads), AVX-512 with streaming stores where the
  * CPU has it.  Bit-identical to mfcd_pack_triplets8.  *bad (host int, caller zeroes it) is set for soft labels
  * or indices out of range.  Needs no GPU.  (The reference moves 28 bytes per sample per step through
- * `x.to(device)`, structure.py:845-846.)  mfcd_host_pack_isa: 512 if the AVX-512 kernel is in use, else 0. */
+ * `x.to(device)`, structure.py:845-846.)  mfcd_host_pack_isa: 512 if the AVX-512 kernel is in use, else 0
+ * (environment MFCD_HOST_PACK_ISA=scalar, read once per process, forces the portable loop). */
 int mfcd_host_pack_triplets8(const mfcd_triplet* rec, int64_t N, uint64_t* out, int32_t threads, int32_t* bad);
 int mfcd_host_pack_isa(void);
 /* Run-length wire format for ONE user-grouped batch of B hard-labelled records with n_items <= 65536

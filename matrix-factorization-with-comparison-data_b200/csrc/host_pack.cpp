@@ -11,6 +11,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -78,6 +79,8 @@ MFCD_AVX512 uint32_t pack_avx512(const mfcd_triplet* rec, int64_t n, uint64_t* o
 typedef uint32_t (*pack_fn)(const mfcd_triplet*, int64_t, uint64_t*);
 
 pack_fn choose_pack() {
+    const char* force = std::getenv("MFCD_HOST_PACK_ISA");          // "scalar": skip the vector kernel (tests)
+    if (force && std::strcmp(force, "scalar") == 0) return pack_scalar;
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq"))
         return pack_avx512;

@@ -147,3 +147,32 @@ def test_c_host_packer_pool_under_concurrent_callers():
         t.join(timeout=120)
     assert not any(t.is_alive() for t in ts), "packer pool deadlocked"
     assert not errors, errors[:3]
+
+
+def test_c_host_packer_scalar_kernel_in_a_fresh_process():
+    """Hosts without AVX-512 take the portable loop; force it (MFCD_HOST_PACK_ISA=scalar is read once per process)
+    and compare whole batches, not just the vector kernel's tail, with the numpy packer."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, %r)
+import mfcd_b200
+from mfcd_b200 import _lib, hostpack
+assert _lib.lib.mfcd_host_pack_isa() == 0, "scalar kernel was not selected"
+rng = np.random.default_rng(5)
+N = 100_003
+rec = hostpack.as_records(rng.integers(0, 1 << 23, N), rng.integers(0, 1 << 20, N), rng.integers(0, 1 << 20, N),
+                          rng.integers(0, 2, N).astype(np.float64))
+for threads in (1, 4):
+    out = np.zeros(N, np.uint64); bad = C.c_int32(0)
+    assert _lib.lib.mfcd_host_pack_triplets8(rec.ctypes.data, N, out.ctypes.data, threads, C.byref(bad)) == 0
+    assert bad.value == 0 and np.array_equal(out, hostpack.pack8(rec))
+rec[77, 3] = np.float32(0.25).view(np.int32)
+assert _lib.lib.mfcd_host_pack_triplets8(rec.ctypes.data, N, out.ctypes.data, 4, C.byref(bad)) == 0 and bad.value == 1
+print("scalar ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MFCD_HOST_PACK_ISA="scalar")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "scalar ok" in r.stdout, r.stdout + r.stderr
